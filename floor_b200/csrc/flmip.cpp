@@ -1,0 +1,763 @@
+// Host side of libfloor_b200_mip.so: a thin C-ABI layer over the CUDA *driver* API (dlopen'd, like floor's
+// src/device/cuda/cuda_api.cpp:46-110) that owns linear image allocations, TMA tensor maps and the launch of
+// the sm_100a kernels embedded as a cubin (mip_kernels.cu).  No CUDA runtime, no CPU fallback.
+#include "../../include/floor_b200_mip.h"
+
+#include <cuda.h> // types and prototypes only -- libcuda is resolved at run time with dlopen/dlsym
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mip_params.h"
+#include "mip_tiling.h"
+
+// the cubin produced from mip_kernels.cu, embedded by cubin_blob.S (cf. `#embed` of mmm.fubar, device_image.cpp:133-139)
+extern "C" const unsigned char flmip_cubin_begin[];
+extern "C" const unsigned char flmip_cubin_end[];
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------------------
+thread_local std::string tl_error;
+int fail(int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	tl_error = buf;
+	return code;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// driver function table
+// ------------------------------------------------------------------------------------------------------
+#define FL_STR2(x) #x
+#define FL_STR(x) FL_STR2(x)
+#define FL_DRIVER_FUNCTIONS(F)                                                                                                 \
+	F(cuInit) F(cuDriverGetVersion) F(cuGetErrorName) F(cuGetErrorString) F(cuDeviceGetCount) F(cuDeviceGet) F(cuDeviceGetName)   \
+	F(cuDeviceGetAttribute) F(cuDeviceTotalMem) F(cuDevicePrimaryCtxRetain) F(cuDevicePrimaryCtxRelease) F(cuCtxPushCurrent)     \
+	F(cuCtxPopCurrent) F(cuMemAlloc) F(cuMemFree) F(cuMemsetD8Async) F(cuMemsetD32Async) F(cuMemcpyHtoDAsync) F(cuMemcpyDtoHAsync) \
+	F(cuMemcpy3DAsync) F(cuMemHostAlloc) F(cuMemFreeHost) F(cuStreamCreate) F(cuStreamDestroy) F(cuStreamSynchronize)            \
+	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
+	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuTensorMapEncodeTiled)
+
+struct driver_api {
+#define FL_DECL(name) decltype(&name) p_##name = nullptr;
+	FL_DRIVER_FUNCTIONS(FL_DECL)
+#undef FL_DECL
+	void* handle = nullptr;
+};
+driver_api cu;
+
+struct device_state {
+	CUdevice dev = 0;
+	CUcontext ctx = nullptr;
+	CUmodule module = nullptr;
+	std::mutex mtx;
+	std::unordered_map<std::string, CUfunction> functions;
+	flmip_device_info info {};
+};
+
+std::once_flag init_once;
+int init_status = FLMIP_ERR_NO_CUDA;
+std::string init_error = "flmip_init() has not been called";
+std::vector<device_state*> devices;
+std::atomic<uint64_t> launch_counter { 0 };
+
+int cu_fail(CUresult r, const char* what) {
+	const char *name = nullptr, *desc = nullptr;
+	if (cu.p_cuGetErrorName) cu.p_cuGetErrorName(r, &name);
+	if (cu.p_cuGetErrorString) cu.p_cuGetErrorString(r, &desc);
+	return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? FLMIP_ERR_OUT_OF_MEMORY : FLMIP_ERR_DRIVER, "%s: %s (%s)", what, name ? name : "?",
+				desc ? desc : "?");
+}
+#define CU_TRY(call, what)                              \
+	do {                                                \
+		const CUresult cu_try_r_ = (call);              \
+		if (cu_try_r_ != CUDA_SUCCESS) return cu_fail(cu_try_r_, what); \
+	} while (0)
+
+void do_init() {
+	const char* names[] = { "libcuda.so.1", "libcuda.so" };
+	for (const char* n : names) {
+		cu.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		if (cu.handle) break;
+	}
+	if (!cu.handle) {
+		init_error = std::string("failed to load libcuda: ") + dlerror();
+		return;
+	}
+#define FL_LOAD(name)                                                                        \
+	cu.p_##name = reinterpret_cast<decltype(&name)>(dlsym(cu.handle, FL_STR(name)));         \
+	if (!cu.p_##name) {                                                                      \
+		init_error = std::string("libcuda lacks ") + FL_STR(name) + " (driver too old?)";    \
+		return;                                                                              \
+	}
+	FL_DRIVER_FUNCTIONS(FL_LOAD)
+#undef FL_LOAD
+	CUresult r = cu.p_cuInit(0);
+	if (r != CUDA_SUCCESS) {
+		const char* name = nullptr;
+		cu.p_cuGetErrorName(r, &name);
+		init_error = std::string("cuInit failed: ") + (name ? name : "?");
+		return;
+	}
+	int version = 0;
+	cu.p_cuDriverGetVersion(&version);
+	int count = 0;
+	if (cu.p_cuDeviceGetCount(&count) != CUDA_SUCCESS || count <= 0) {
+		init_error = "no CUDA device";
+		return;
+	}
+	for (int i = 0; i < count; ++i) {
+		auto* ds = new device_state;
+		if (cu.p_cuDeviceGet(&ds->dev, i) != CUDA_SUCCESS) { init_error = "cuDeviceGet failed"; return; }
+		auto attr = [&](CUdevice_attribute a) {
+			int v = 0;
+			cu.p_cuDeviceGetAttribute(&v, a, ds->dev);
+			return (uint32_t)v;
+		};
+		cu.p_cuDeviceGetName(ds->info.name, sizeof(ds->info.name), ds->dev);
+		size_t mem = 0;
+		cu.p_cuDeviceTotalMem(&mem, ds->dev);
+		ds->info.global_mem_size = mem;
+		ds->info.sm_major = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR);
+		ds->info.sm_minor = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR);
+		ds->info.units = attr(CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT);
+		ds->info.max_total_local_size = attr(CU_DEVICE_ATTRIBUTE_MAX_THREADS_PER_BLOCK);
+		ds->info.max_image_2d_dim[0] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE2D_WIDTH);
+		ds->info.max_image_2d_dim[1] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE2D_HEIGHT);
+		ds->info.max_image_3d_dim[0] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE3D_WIDTH);
+		ds->info.max_image_3d_dim[1] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE3D_HEIGHT);
+		ds->info.max_image_3d_dim[2] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE3D_DEPTH);
+		ds->info.max_mip_levels = FLMIP_MAX_LEVELS;
+		ds->info.driver_version = (uint32_t)version;
+		devices.push_back(ds);
+	}
+	init_status = FLMIP_OK;
+	init_error.clear();
+}
+
+int ensure_init() {
+	std::call_once(init_once, do_init);
+	if (init_status != FLMIP_OK) return fail(init_status, "%s", init_error.c_str());
+	return FLMIP_OK;
+}
+
+int get_device(int device, device_state** out) {
+	const int rc = ensure_init();
+	if (rc != FLMIP_OK) return rc;
+	if (device < 0 || (size_t)device >= devices.size()) return fail(FLMIP_ERR_INVALID, "invalid device index %d (have %zu)", device, devices.size());
+	device_state* ds = devices[(size_t)device];
+	if (!ds->ctx) {
+		std::lock_guard<std::mutex> lock(ds->mtx);
+		if (!ds->ctx) {
+			// primary context: shared with any CUDA-runtime user in the process (floor creates its own: cuda_context.cpp:117-124)
+			CUcontext ctx = nullptr;
+			CU_TRY(cu.p_cuDevicePrimaryCtxRetain(&ctx, ds->dev), "cuDevicePrimaryCtxRetain");
+			ds->ctx = ctx;
+		}
+	}
+	*out = ds;
+	return FLMIP_OK;
+}
+
+// every entry point makes the device's context current for the calling thread (cf. cuda_function.cpp:83-87)
+struct ctx_guard {
+	bool pushed = false;
+	int push(device_state* ds) {
+		CU_TRY(cu.p_cuCtxPushCurrent(ds->ctx), "cuCtxPushCurrent");
+		pushed = true;
+		return FLMIP_OK;
+	}
+	~ctx_guard() {
+		if (pushed) {
+			CUcontext old = nullptr;
+			cu.p_cuCtxPopCurrent(&old);
+		}
+	}
+};
+#define WITH_DEVICE(device)                                           \
+	device_state* ds = nullptr;                                       \
+	{                                                                 \
+		const int wd_rc_ = get_device((device), &ds);                 \
+		if (wd_rc_ != FLMIP_OK) return wd_rc_;                        \
+	}                                                                 \
+	ctx_guard guard;                                                  \
+	{                                                                 \
+		const int wd_rc_ = guard.push(ds);                            \
+		if (wd_rc_ != FLMIP_OK) return wd_rc_;                        \
+	}
+
+int get_function(device_state* ds, const std::string& name, uint32_t dynamic_smem, CUfunction* out) {
+	std::lock_guard<std::mutex> lock(ds->mtx);
+	if (!ds->module) {
+		if (ds->info.sm_major != 10) {
+			return fail(FLMIP_ERR_UNSUPPORTED, "device '%s' is sm_%u%u; this library only carries sm_100a code", ds->info.name, ds->info.sm_major,
+						ds->info.sm_minor);
+		}
+		CU_TRY(cu.p_cuModuleLoadData(&ds->module, flmip_cubin_begin), "cuModuleLoadData(embedded cubin)");
+	}
+	auto it = ds->functions.find(name);
+	if (it == ds->functions.end()) {
+		CUfunction fn = nullptr;
+		CU_TRY(cu.p_cuModuleGetFunction(&fn, ds->module, name.c_str()), ("cuModuleGetFunction " + name).c_str());
+		if (dynamic_smem > 48u * 1024u) {
+			CU_TRY(cu.p_cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dynamic_smem), "cuFuncSetAttribute(smem)");
+		}
+		it = ds->functions.emplace(name, fn).first;
+	}
+	*out = it->second;
+	return FLMIP_OK;
+}
+
+int launch(CUfunction fn, uint64_t grid, uint32_t block, uint32_t smem, CUstream stream, void** args) {
+	if (grid == 0) return FLMIP_OK;
+	if (grid > 0x7FFFFFFFull) return fail(FLMIP_ERR_INVALID, "grid of %llu blocks exceeds the launch limit", (unsigned long long)grid);
+	CU_TRY(cu.p_cuLaunchKernel(fn, (unsigned)grid, 1, 1, block, 1, 1, smem, stream, args, nullptr), "cuLaunchKernel");
+	launch_counter.fetch_add(1, std::memory_order_relaxed);
+	return FLMIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// IMAGE_TYPE decoding (bit layout: include/floor/device/backend/image_types.hpp:24-236)
+// ------------------------------------------------------------------------------------------------------
+constexpr uint64_t T_FORMAT_MASK = 0x3Full, T_COMPRESSION_MASK = 0x3C0ull, T_DATA_TYPE_MASK = 0x3000ull;
+constexpr uint64_t T_INT = 0x1000ull, T_UINT = 0x2000ull, T_FLOAT = 0x3000ull;
+constexpr uint64_t T_FLAG_ARRAY = 1ull << 20, T_FLAG_MSAA = 1ull << 22, T_FLAG_CUBE = 1ull << 23, T_FLAG_DEPTH = 1ull << 24,
+				   T_FLAG_STENCIL = 1ull << 25, T_FLAG_MIPMAPPED = 1ull << 27, T_FLAG_NORMALIZED = 1ull << 30;
+constexpr uint32_t FMT_8 = 11, FMT_16 = 18, FMT_32 = 22;
+
+bool is_pot(uint32_t v) { return v != 0 && (v & (v - 1)) == 0; }
+
+} // namespace
+
+struct flmip_image_s {
+	int device = 0;
+	uint64_t type = 0;
+	uint32_t dim[4] = { 0, 0, 0, 0 };
+	uint32_t dc = 0, channels = 0, bpc = 0, bpp = 0, layers = 0, level_count = 0, elem_kind = 0, no_double = 0;
+	flmip_level_info levels[FLMIP_MAX_LEVELS] {};
+	uint64_t total_size = 0;
+	CUdeviceptr mem = 0, counters = 0;
+	// single-pass plan
+	bool fast = false;
+	uint32_t fast_level_count = 0; // levels [0, fast_level_count) are produced by the single-pass launch
+	flmip_fast_params fast_params {};
+	flmip_tiling_rt tiling {};
+	alignas(64) CUtensorMap tmap {};
+	std::string fast_name;
+};
+
+namespace {
+
+// image_types.hpp:694-712
+uint32_t mip_level_count_for(const uint32_t dim[4], uint64_t type, uint32_t dc) {
+	if (!(type & T_FLAG_MIPMAPPED)) return 1;
+	uint32_t m = dim[0];
+	if (dc >= 2 && dim[1] > m) m = dim[1];
+	if (dc >= 3 && dim[2] > m) m = dim[2];
+	if (m <= 1) return 1;
+	uint32_t n = 0;
+	while (m) { ++n; m >>= 1; }
+	return n; // 32 - clz(prev_pot(max_dim))
+}
+
+int decode_type(flmip_image_s& im) {
+	const uint64_t t = im.type;
+	im.dc = (uint32_t)((t >> 16) & 3u);
+	im.channels = (uint32_t)((t >> 14) & 3u) + 1u;
+	const uint32_t fmt = (uint32_t)(t & T_FORMAT_MASK);
+	im.bpc = fmt == FMT_8 ? 8 : fmt == FMT_16 ? 16 : fmt == FMT_32 ? 32 : 0;
+	if (im.dc < 1 || im.dc > 3) return fail(FLMIP_ERR_INVALID, "invalid image dimensionality in type %#llx", (unsigned long long)t);
+	if (t & T_COMPRESSION_MASK) return fail(FLMIP_ERR_UNSUPPORTED, "compressed images cannot be minified (device_image.hpp:519-525)");
+	if (t & T_FLAG_MSAA) return fail(FLMIP_ERR_UNSUPPORTED, "msaa is not supported (mip_map_minify.hpp:95)");
+	if (t & T_FLAG_STENCIL) return fail(FLMIP_ERR_UNSUPPORTED, "stencil images have no minification kernel");
+	if (im.bpc == 0) return fail(FLMIP_ERR_UNSUPPORTED, "unsupported image format %u (8/16/32 bit per channel only)", fmt);
+	if (im.channels == 3) return fail(FLMIP_ERR_UNSUPPORTED, "3-channel images are unsupported with CUDA (cuda_image.cpp:173-180)");
+	if (im.dc == 3 && (t & (T_FLAG_ARRAY | T_FLAG_CUBE))) return fail(FLMIP_ERR_UNSUPPORTED, "3D array images have no minification kernel");
+	const uint64_t dt = t & T_DATA_TYPE_MASK;
+	const bool norm = (t & T_FLAG_NORMALIZED) != 0;
+	if (dt == T_FLOAT) {
+		if (im.bpc == 32) im.elem_kind = FLMIP_EK_F32;
+		else if (im.bpc == 16) im.elem_kind = FLMIP_EK_F16;
+		else return fail(FLMIP_ERR_UNSUPPORTED, "8-bit float formats do not exist");
+	} else if (dt == T_UINT || dt == T_INT) {
+		const bool s = dt == T_INT;
+		if (norm) {
+			if (im.bpc == 8) im.elem_kind = s ? FLMIP_EK_SNORM8 : FLMIP_EK_UNORM8;
+			else if (im.bpc == 16) im.elem_kind = s ? FLMIP_EK_SNORM16 : FLMIP_EK_UNORM16;
+			else return fail(FLMIP_ERR_UNSUPPORTED, "32-bit normalized formats are not supported on CUDA");
+		} else {
+			im.elem_kind = im.bpc == 8 ? (s ? FLMIP_EK_I8 : FLMIP_EK_U8) : im.bpc == 16 ? (s ? FLMIP_EK_I16 : FLMIP_EK_U16) : (s ? FLMIP_EK_I32 : FLMIP_EK_U32);
+		}
+	} else {
+		return fail(FLMIP_ERR_INVALID, "image type %#llx has no data type", (unsigned long long)t);
+	}
+	if (t & T_FLAG_DEPTH) {
+		// only libfloor_mip_map_minify_IMAGE_DEPTH[_ARRAY]_FLOAT exist (mip_map_minify.hpp:22-30)
+		if (!(im.elem_kind == FLMIP_EK_F32 && im.channels == 1)) return fail(FLMIP_ERR_UNSUPPORTED, "only D32F depth images can be minified");
+	}
+	im.bpp = im.bpc / 8u * im.channels;
+	return FLMIP_OK;
+}
+
+// levels a cascade adds when it starts with a region of (w, h, d) texels at `lvl`
+uint32_t simulate_cascade(uint32_t w, uint32_t h, uint32_t d, bool is3d, uint32_t lvl, uint32_t level_count) {
+	while (lvl + 1 < level_count && w >= 2 && h >= 2 && (!is3d || d >= 2)) {
+		w >>= 1; h >>= 1; if (is3d) d >>= 1;
+		++lvl;
+	}
+	return lvl;
+}
+
+bool next_level_has_texels(const flmip_image_s& im, uint32_t lvl) {
+	const uint32_t n = lvl + 1;
+	if (n >= im.level_count) return false;
+	const flmip_level_info& li = im.levels[n];
+	return li.dim[0] != 0 && (im.dc < 2 || li.dim[1] != 0) && (im.dc < 3 || li.dim[2] != 0);
+}
+
+// decides whether the single-pass kernel applies and how far it gets; mirrors fast_body() in mip_kernels.cu
+int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
+	im.fast = false;
+	if (flags & FLMIP_IMAGE_FORCE_GENERIC) return FLMIP_OK;
+	if (im.level_count < 2 || im.dc < 2) return FLMIP_OK;
+	const bool is3d = im.dc == 3;
+	const uint32_t W = im.dim[0], H = im.dim[1], D = is3d ? im.dim[2] : 1u;
+	if (!is_pot(W) || !is_pot(H) || !is_pot(D)) return FLMIP_OK;
+	const flmip_tiling_rt tl = flmip_tiling_lookup(im.bpp, im.dc);
+	if (W < tl.tx || H < tl.ty || D < tl.tz) return FLMIP_OK;
+	if ((uint64_t)W * im.bpp >= (1ull << 32) * 4ull) return FLMIP_OK;
+
+	flmip_fast_params& P = im.fast_params;
+	memset(&P, 0, sizeof(P));
+	P.base = im.mem;
+	for (uint32_t l = 0; l < FLMIP_MAX_LEVELS; ++l) P.level_off[l] = l < im.level_count ? im.levels[l].offset : 0;
+	P.dim[0] = W; P.dim[1] = H; P.dim[2] = D;
+	P.tiles[0] = W / tl.tx; P.tiles[1] = H / tl.ty; P.tiles[2] = D / tl.tz;
+	for (int i = 0; i < 3; ++i) P.groups[i] = (P.tiles[i] + tl.group - 1) / tl.group;
+	P.layers = im.layers;
+	P.no_double = im.no_double;
+
+	// tile stage
+	uint32_t lvl = simulate_cascade(tl.tx, tl.ty, tl.tz, is3d, 0, im.level_count);
+	uint32_t covered = lvl;
+	if (next_level_has_texels(im, lvl)) {
+		// group stage
+		const uint32_t ntx = P.tiles[0] < tl.group ? P.tiles[0] : tl.group, nty = P.tiles[1] < tl.group ? P.tiles[1] : tl.group,
+					   ntz = P.tiles[2] < tl.group ? P.tiles[2] : tl.group;
+		lvl = simulate_cascade((tl.tx >> lvl) * ntx, (tl.ty >> lvl) * nty, (tl.tz >> lvl) * ntz, is3d, lvl, im.level_count);
+		covered = lvl;
+		if (next_level_has_texels(im, lvl)) {
+			// layer stage: the whole level must fit into the cascade scratch, else the general path finishes the chain
+			const uint64_t patch = (uint64_t)(W >> lvl) * (H >> lvl) * (is3d ? (D >> lvl) : 1u) * im.bpp;
+			if (patch <= tl.cascade_bytes) covered = simulate_cascade(W >> lvl, H >> lvl, is3d ? D >> lvl : 1u, is3d, lvl, im.level_count);
+		}
+	}
+	im.fast_level_count = covered + 1;
+	P.level_count = im.fast_level_count;
+	im.tiling = tl;
+
+	// counters: one per tile group and one per layer, zeroed once; the kernel resets what it uses
+	const uint64_t n_counters = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2] + im.layers;
+	CU_TRY(cu.p_cuMemAlloc(&im.counters, n_counters * sizeof(uint32_t)), "cuMemAlloc(counters)");
+	CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, nullptr), "cuMemsetD32Async(counters)");
+	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
+	P.counters = im.counters;
+
+	// TMA descriptor over level 0: rank 3 in uint32 units -- (x, y, layer) for 2D / array / cube, (x, y, z) for volumes
+	const cuuint64_t row_bytes = (cuuint64_t)W * im.bpp;
+	cuuint64_t gdim[3] = { row_bytes / 4u, H, is3d ? D : im.layers };
+	cuuint64_t gstride[2] = { row_bytes, row_bytes * H };
+	cuuint32_t box[3] = { tl.tile_bytes_x / 4u, tl.ty, is3d ? tl.tz : 1u };
+	cuuint32_t estride[3] = { 1, 1, 1 };
+	CU_TRY(cu.p_cuTensorMapEncodeTiled(&im.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, reinterpret_cast<void*>(im.mem), gdim, gstride, box, estride,
+									   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+									   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+		   "cuTensorMapEncodeTiled");
+
+	char name[64];
+	snprintf(name, sizeof(name), "flmip_fast%ud_k%u_c%u", im.dc, im.elem_kind, im.channels);
+	im.fast_name = name;
+	CUfunction fn = nullptr;
+	const int rc = get_function(ds, im.fast_name, tl.smem_bytes, &fn); // resolve now: fail at creation, not at first use
+	if (rc != FLMIP_OK) return rc;
+	im.fast = true;
+	return FLMIP_OK;
+}
+
+int launch_generic_level(flmip_image_s& im, device_state* ds, uint32_t level, CUstream stream) {
+	const flmip_level_info &src = im.levels[level - 1], &dst = im.levels[level];
+	flmip_generic_params G;
+	memset(&G, 0, sizeof(G));
+	uint64_t texels = 1;
+	for (uint32_t d = 0; d < im.dc; ++d) {
+		if (dst.dim[d] == 0) return FLMIP_OK; // empty level (zero dim quirk): the reference launches zero work-items
+		texels *= dst.dim[d];
+	}
+	G.base = im.mem;
+	G.src_off = src.offset; G.dst_off = dst.offset;
+	G.src_slice = src.slice_size; G.dst_slice = dst.slice_size;
+	G.total = texels * im.layers;
+	for (uint32_t d = 0; d < 3; ++d) {
+		G.src_dim[d] = src.dim[d]; G.dst_dim[d] = dst.dim[d];
+		// device_image.cpp:311-312 and host_image.cpp:96-107, evaluated in IEEE fp32 on the host
+		G.inv_prev[d] = 1.0f / (float)src.dim[d];
+		G.fdim[d] = src.dim[d] > 0 ? (float)src.dim[d] : 0.0f;
+		G.fdim_excl[d] = src.dim[d] > 0 ? nextafterf((float)src.dim[d], 0.0f) : 0.0f;
+	}
+	G.dc = im.dc; G.layers = im.layers; G.elem_kind = im.elem_kind; G.channels = im.channels; G.no_double = im.no_double;
+	CUfunction fn = nullptr;
+	const int rc = get_function(ds, "flmip_generic", 0, &fn);
+	if (rc != FLMIP_OK) return rc;
+	void* args[] = { &G };
+	return launch(fn, (G.total + 255u) / 256u, 256, 0, stream, args);
+}
+
+int check_image(flmip_image img) {
+	if (!img) return fail(FLMIP_ERR_INVALID, "null image handle");
+	return FLMIP_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int flmip_init(void) { return ensure_init(); }
+
+int flmip_device_count(void) {
+	if (ensure_init() != FLMIP_OK) return 0;
+	return (int)devices.size();
+}
+
+int flmip_get_device_info(int device, flmip_device_info* out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	const int rc = ensure_init();
+	if (rc != FLMIP_OK) return rc;
+	if (device < 0 || (size_t)device >= devices.size()) return fail(FLMIP_ERR_INVALID, "invalid device index %d", device);
+	*out = devices[(size_t)device]->info;
+	return FLMIP_OK;
+}
+
+const char* flmip_last_error_string(void) { return tl_error.c_str(); }
+uint64_t flmip_launch_count(void) { return launch_counter.load(std::memory_order_relaxed); }
+
+int flmip_stream_create(int device, flmip_stream* out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	WITH_DEVICE(device)
+	CUstream s = nullptr;
+	CU_TRY(cu.p_cuStreamCreate(&s, CU_STREAM_NON_BLOCKING), "cuStreamCreate"); // cuda_context.cpp:418-437
+	*out = s;
+	return FLMIP_OK;
+}
+int flmip_stream_destroy(int device, flmip_stream stream) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuStreamDestroy((CUstream)stream), "cuStreamDestroy");
+	return FLMIP_OK;
+}
+int flmip_stream_sync(int device, flmip_stream stream) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuStreamSynchronize((CUstream)stream), "cuStreamSynchronize");
+	return FLMIP_OK;
+}
+int flmip_event_create(int device, flmip_event* out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	WITH_DEVICE(device)
+	CUevent e = nullptr;
+	CU_TRY(cu.p_cuEventCreate(&e, CU_EVENT_DEFAULT), "cuEventCreate");
+	*out = e;
+	return FLMIP_OK;
+}
+int flmip_event_record(int device, flmip_event ev, flmip_stream stream) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuEventRecord((CUevent)ev, (CUstream)stream), "cuEventRecord");
+	return FLMIP_OK;
+}
+int flmip_event_sync(int device, flmip_event ev) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuEventSynchronize((CUevent)ev), "cuEventSynchronize");
+	return FLMIP_OK;
+}
+int flmip_event_elapsed_ms(int device, flmip_event start, flmip_event stop, float* ms) {
+	if (!ms) return fail(FLMIP_ERR_INVALID, "null output");
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuEventElapsedTime(ms, (CUevent)start, (CUevent)stop), "cuEventElapsedTime");
+	return FLMIP_OK;
+}
+int flmip_event_destroy(int device, flmip_event ev) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuEventDestroy((CUevent)ev), "cuEventDestroy");
+	return FLMIP_OK;
+}
+int flmip_host_alloc(int device, size_t size, void** out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuMemHostAlloc(out, size, CU_MEMHOSTALLOC_PORTABLE), "cuMemHostAlloc");
+	return FLMIP_OK;
+}
+int flmip_host_free(int device, void* ptr) {
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuMemFreeHost(ptr), "cuMemFreeHost");
+	return FLMIP_OK;
+}
+
+int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags, flmip_image* out) {
+	if (!out || !image_dim) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = nullptr;
+	auto im = new flmip_image_s;
+	im->device = device;
+	im->type = image_type;
+	memcpy(im->dim, image_dim, sizeof(im->dim));
+	im->no_double = (flags & FLMIP_IMAGE_NO_DOUBLE) ? 1u : 0u;
+	int rc = decode_type(*im);
+	if (rc != FLMIP_OK) { delete im; return rc; }
+	if (im->dim[0] == 0 || (im->dc >= 2 && im->dim[1] == 0) || (im->dc >= 3 && im->dim[2] == 0)) {
+		delete im;
+		return fail(FLMIP_ERR_INVALID, "image dimensions must be non-zero");
+	}
+	// image_types.hpp:716-726
+	const bool is_array = (image_type & T_FLAG_ARRAY) != 0, is_cube = (image_type & T_FLAG_CUBE) != 0;
+	im->layers = !is_array ? 1u : (im->dc == 1 ? im->dim[1] : (im->dc == 2 ? im->dim[2] : im->dim[3]));
+	if (is_cube) {
+		im->layers *= 6u;
+		if (im->dim[0] != im->dim[1]) { delete im; return fail(FLMIP_ERR_INVALID, "cube map side width and height must be equal (cuda_image.cpp:187-191)"); }
+	}
+	if (im->layers == 0) { delete im; return fail(FLMIP_ERR_INVALID, "array image without layers"); }
+	// device_image.hpp:483-485
+	im->level_count = mip_level_count_for(im->dim, image_type, im->dc);
+	if (mip_level_limit > 0 && mip_level_limit < im->level_count) im->level_count = mip_level_limit;
+	if (im->level_count > FLMIP_MAX_LEVELS) { delete im; return fail(FLMIP_ERR_UNSUPPORTED, "more than %u mip levels", FLMIP_MAX_LEVELS); }
+	// level table: dim >> level without max(1) (host_image.cpp:75-88, image_types.hpp:751-766), 64-bit offsets
+	uint64_t off = 0;
+	for (uint32_t l = 0; l < im->level_count; ++l) {
+		flmip_level_info& li = im->levels[l];
+		li.dim[0] = im->dim[0] >> l;
+		li.dim[1] = im->dc >= 2 ? im->dim[1] >> l : 0;
+		li.dim[2] = im->dc >= 3 ? im->dim[2] >> l : 0;
+		uint64_t texels = li.dim[0];
+		if (im->dc >= 2) texels *= li.dim[1];
+		if (im->dc >= 3) texels *= li.dim[2];
+		li.slice_size = texels * im->bpp;
+		li.size = li.slice_size * im->layers;
+		li.offset = off;
+		off += li.size;
+	}
+	im->total_size = off;
+
+	device_state* ds = nullptr;
+	rc = get_device(device, &ds);
+	if (rc != FLMIP_OK) { delete im; return rc; }
+	ctx_guard guard;
+	rc = guard.push(ds);
+	if (rc != FLMIP_OK) { delete im; return rc; }
+	CUresult r = cu.p_cuMemAlloc(&im->mem, im->total_size);
+	if (r != CUDA_SUCCESS) { delete im; return cu_fail(r, "cuMemAlloc(image)"); }
+	rc = plan_fast(*im, ds, flags);
+	if (rc != FLMIP_OK) {
+		if (im->counters) cu.p_cuMemFree(im->counters);
+		cu.p_cuMemFree(im->mem);
+		delete im;
+		return rc;
+	}
+	*out = im;
+	return FLMIP_OK;
+}
+
+int flmip_image_destroy(flmip_image img) {
+	if (!img) return FLMIP_OK;
+	WITH_DEVICE(img->device)
+	if (img->counters) cu.p_cuMemFree(img->counters);
+	if (img->mem) cu.p_cuMemFree(img->mem);
+	delete img;
+	return FLMIP_OK;
+}
+
+int flmip_image_mip_level_count(flmip_image img, uint32_t* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = img->level_count;
+	return FLMIP_OK;
+}
+int flmip_image_layer_count(flmip_image img, uint32_t* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = img->layers;
+	return FLMIP_OK;
+}
+int flmip_image_data_size(flmip_image img, uint64_t* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = img->total_size;
+	return FLMIP_OK;
+}
+int flmip_image_get_level_info(flmip_image img, uint32_t level, flmip_level_info* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	if (level >= img->level_count) return fail(FLMIP_ERR_INVALID, "mip level %u out of range (%u levels)", level, img->level_count);
+	*out = img->levels[level];
+	return FLMIP_OK;
+}
+int flmip_image_device_ptr(flmip_image img, uint64_t* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = (uint64_t)img->mem;
+	return FLMIP_OK;
+}
+int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast_levels, uint32_t* launches) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	uint32_t n = 0;
+	const uint32_t first_generic = img->fast ? img->fast_level_count : 1u;
+	if (img->fast) ++n;
+	for (uint32_t l = first_generic; l < img->level_count; ++l) {
+		const flmip_level_info& li = img->levels[l];
+		if (li.size != 0) ++n;
+	}
+	if (uses_single_pass) *uses_single_pass = img->fast ? 1u : 0u;
+	if (fast_levels) *fast_levels = img->fast ? img->fast_level_count : 0u;
+	if (launches) *launches = n;
+	return FLMIP_OK;
+}
+
+int flmip_image_upload(flmip_image img, const void* src, size_t src_size, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (!src) return fail(FLMIP_ERR_INVALID, "null source");
+	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
+	const uint64_t begin = img->levels[level_first].offset, end = img->levels[level_last].offset + img->levels[level_last].size;
+	if (src_size < end - begin) return fail(FLMIP_ERR_INVALID, "image upload: insufficient host data (%zu < %llu)", src_size, (unsigned long long)(end - begin));
+	if (end == begin) return FLMIP_OK;
+	WITH_DEVICE(img->device)
+	CU_TRY(cu.p_cuMemcpyHtoDAsync(img->mem + begin, src, end - begin, (CUstream)stream), "cuMemcpyHtoDAsync");
+	return FLMIP_OK;
+}
+
+int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (!dst) return fail(FLMIP_ERR_INVALID, "null destination");
+	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
+	const uint64_t begin = img->levels[level_first].offset, end = img->levels[level_last].offset + img->levels[level_last].size;
+	if (dst_size < end - begin) return fail(FLMIP_ERR_INVALID, "image download: insufficient host buffer (%zu < %llu)", dst_size, (unsigned long long)(end - begin));
+	if (end == begin) return FLMIP_OK;
+	WITH_DEVICE(img->device)
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(dst, img->mem + begin, end - begin, (CUstream)stream), "cuMemcpyDtoHAsync");
+	return FLMIP_OK;
+}
+
+int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
+					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (!src || !offset || !extent || !mip_level_range || !layer_range) return fail(FLMIP_ERR_INVALID, "null argument");
+	// write_check (device_image.cpp:503-547)
+	if (mip_level_range[0] > mip_level_range[1] || mip_level_range[1] >= img->level_count) return fail(FLMIP_ERR_INVALID, "image write: invalid mip level range");
+	if (layer_range[0] > layer_range[1] || layer_range[1] >= img->layers) return fail(FLMIP_ERR_INVALID, "image write: invalid layer range");
+	for (uint32_t d = 0; d < img->dc; ++d) {
+		if (extent[d] == 0 || (uint64_t)offset[d] + extent[d] > img->dim[d]) return fail(FLMIP_ERR_INVALID, "image write: offset + extent out of bounds in dim %u", d);
+	}
+	WITH_DEVICE(img->device)
+	const uint32_t n_layers = layer_range[1] - layer_range[0] + 1u;
+	const uint8_t* cur = static_cast<const uint8_t*>(src);
+	size_t left = src_size;
+	for (uint32_t level = mip_level_range[0]; level <= mip_level_range[1]; ++level) {
+		const flmip_level_info& li = img->levels[level];
+		// derive the mip extent from the user-specified extent (cuda_image.cpp:609-611)
+		uint32_t e[3] = { 1, 1, 1 }, o[3] = { 0, 0, 0 };
+		for (uint32_t d = 0; d < img->dc; ++d) {
+			e[d] = extent[d] >> level;
+			if (e[d] == 0) e[d] = 1;
+			o[d] = offset[d] >> level;
+		}
+		if (li.size == 0) continue;
+		// the source holds this level of an image of size `extent` with n_layers layers, tightly packed
+		const uint64_t src_row = (uint64_t)e[0] * img->bpp, src_slice = src_row * e[1] * e[2];
+		const uint64_t bytes = src_slice * n_layers;
+		if (left < bytes) return fail(FLMIP_ERR_INVALID, "image write: insufficient host data at mip-level %u", level);
+		for (uint32_t layer = 0; layer < n_layers; ++layer) {
+			CUDA_MEMCPY3D c;
+			memset(&c, 0, sizeof(c));
+			c.srcMemoryType = CU_MEMORYTYPE_HOST;
+			c.srcHost = cur + layer * src_slice;
+			c.srcPitch = src_row;
+			c.srcHeight = e[1];
+			c.dstMemoryType = CU_MEMORYTYPE_DEVICE;
+			c.dstDevice = img->mem + li.offset + (uint64_t)(layer_range[0] + layer) * li.slice_size;
+			c.dstPitch = (uint64_t)li.dim[0] * img->bpp;
+			c.dstHeight = img->dc >= 2 ? li.dim[1] : 1;
+			c.dstXInBytes = (uint64_t)o[0] * img->bpp;
+			c.dstY = o[1];
+			c.dstZ = o[2];
+			c.WidthInBytes = src_row;
+			c.Height = e[1];
+			c.Depth = e[2];
+			CU_TRY(cu.p_cuMemcpy3DAsync(&c, (CUstream)stream), "cuMemcpy3DAsync(image write)");
+		}
+		cur += bytes;
+		left -= bytes;
+	}
+	return FLMIP_OK;
+}
+
+int flmip_image_zero(flmip_image img, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	WITH_DEVICE(img->device)
+	CU_TRY(cu.p_cuMemsetD8Async(img->mem, 0, img->total_size, (CUstream)stream), "cuMemsetD8Async");
+	return FLMIP_OK;
+}
+
+int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (img->level_count < 2 || first_level + 1 >= img->level_count) return FLMIP_OK; // nothing to generate
+	WITH_DEVICE(img->device)
+	uint32_t next = first_level + 1; // first level still to be produced
+	if (img->fast && first_level == 0) {
+		CUfunction fn = nullptr;
+		int rc = get_function(ds, img->fast_name, img->tiling.smem_bytes, &fn);
+		if (rc != FLMIP_OK) return rc;
+		const flmip_fast_params& P = img->fast_params;
+		void* args[] = { &img->tmap, const_cast<flmip_fast_params*>(&P) };
+		const uint64_t grid = (uint64_t)P.tiles[0] * P.tiles[1] * P.tiles[2] * img->layers;
+		rc = launch(fn, grid, 256, img->tiling.smem_bytes, (CUstream)stream, args);
+		if (rc != FLMIP_OK) return rc;
+		next = img->fast_level_count;
+	}
+	// general path: one launch per remaining level, stream-ordered (the reference syncs the host after each: device_image.cpp:322)
+	for (uint32_t level = next; level < img->level_count; ++level) {
+		const int rc = launch_generic_level(*img, ds, level, (CUstream)stream);
+		if (rc != FLMIP_OK) return rc;
+	}
+	return FLMIP_OK;
+}
+
+int flmip_mip_chain_generate(flmip_image img, flmip_stream stream) { return flmip_mip_chain_generate_from(img, 0, stream); }
+
+int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	WITH_DEVICE(img->device)
+	flmip_fill_params F;
+	memset(&F, 0, sizeof(F));
+	F.dst = img->mem;
+	F.elems_per_layer = img->levels[0].slice_size / (img->bpc / 8u);
+	F.config_id = config_id;
+	F.layer_id0 = layer_id0;
+	F.layers = img->layers;
+	F.elem_kind = img->elem_kind;
+	CUfunction fn = nullptr;
+	const int rc = get_function(ds, "flmip_fill", 0, &fn);
+	if (rc != FLMIP_OK) return rc;
+	const uint64_t total = F.elems_per_layer * F.layers;
+	uint64_t grid = (total + 255u) / 256u;
+	const uint64_t cap = (uint64_t)ds->info.units * 32u;
+	if (grid > cap) grid = cap;
+	void* args[] = { &F };
+	return launch(fn, grid, 256, 0, (CUstream)stream, args);
+}
+
+} // extern "C"

@@ -1,0 +1,55 @@
+// Parameter blocks shared by the host C-ABI layer (flmip.cpp) and the sm_100a kernels (mip_kernels.cu).
+// Plain C structs: they are passed by value through cuLaunchKernelEx.
+#pragma once
+#include <stdint.h>
+
+#define FLMIP_MAX_LEVELS 16u // == host_limits::max_mip_levels of the reference (host_image.hpp:462-479)
+
+// storage element kinds the path supports (reference format LUT: src/device/cuda/cuda_image.cpp:197-248,
+// normalized variants: include/floor/device/backend/host_image.hpp:487-561)
+enum flmip_elem_kind : uint32_t {
+	FLMIP_EK_F32 = 0,
+	FLMIP_EK_F16,
+	FLMIP_EK_UNORM8,
+	FLMIP_EK_SNORM8,
+	FLMIP_EK_UNORM16,
+	FLMIP_EK_SNORM16,
+	FLMIP_EK_U8,
+	FLMIP_EK_I8,
+	FLMIP_EK_U16,
+	FLMIP_EK_I16,
+	FLMIP_EK_U32,
+	FLMIP_EK_I32,
+	FLMIP_EK_COUNT
+};
+
+// one destination level, any size (NPOT capable): the general path
+struct flmip_generic_params {
+	uint64_t base;                 // device address of the image
+	uint64_t src_off, dst_off;     // byte offsets of level-1 / level
+	uint64_t src_slice, dst_slice; // bytes of one layer in either level
+	uint64_t total;                // dst texels per layer * layers
+	uint32_t src_dim[3], dst_dim[3];
+	float inv_prev[3];  // 1.0f / float(src_dim)   (device_image.cpp:311-312)
+	float fdim[3];      // float(src_dim)          (host_image.cpp:96-101)
+	float fdim_excl[3]; // nextafterf(fdim, 0)     (host_image.cpp:102-107)
+	uint32_t dc, layers, elem_kind, channels, no_double;
+};
+
+// single-pass multi-level downsampler (power-of-two images)
+struct flmip_fast_params {
+	uint64_t base;
+	uint64_t level_off[FLMIP_MAX_LEVELS];
+	uint64_t counters;  // uint32[layers * groups] group counters, then uint32[layers] layer counters
+	uint32_t dim[3];    // level-0 size in texels (z = 1 for 2D)
+	uint32_t tiles[3];  // tiles per layer
+	uint32_t groups[3]; // tile groups per layer
+	uint32_t layers, level_count, no_double, pad;
+};
+
+struct flmip_fill_params {
+	uint64_t dst;             // device address of level 0 of the first layer to fill
+	uint64_t elems_per_layer; // texels * channels
+	uint64_t config_id, layer_id0;
+	uint32_t layers, elem_kind;
+};

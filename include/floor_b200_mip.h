@@ -1,0 +1,120 @@
+/*
+ * floor_b200_mip.h -- C-ABI of the B200-native mip-chain library (libfloor_b200_mip.so).
+ *
+ * libfloor has no C ABI / plugin interface for this path: the seam is the C++ virtual
+ * fl::device_image::generate_mip_map_chain (include/floor/device/device_image.hpp:161-162).  This layer
+ * sits where floor keeps its dlsym'd driver table (src/device/cuda/cuda_api.cpp:46-110): below the C++
+ * device_context / device_queue / device_image classes (mirrored in include/floor_b200/) and above the
+ * CUDA driver API.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: extern "C", plain pointers and sizes, opaque handles, int status (0 = ok, < 0 = error),
+ * no exceptions; flmip_last_error_string() returns the calling thread's last message.  There is no CPU
+ * fallback: without a usable libcuda / GPU every compute entry point fails with FLMIP_ERR_NO_CUDA.
+ */
+#ifndef FLOOR_B200_MIP_H
+#define FLOOR_B200_MIP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLMIP_OK 0
+#define FLMIP_ERR_NO_CUDA (-1)      /* libcuda missing / cuInit failed / no device */
+#define FLMIP_ERR_INVALID (-2)      /* bad argument */
+#define FLMIP_ERR_UNSUPPORTED (-3)  /* image type has no minification kernel (reference: device_image.cpp:278-283) */
+#define FLMIP_ERR_DRIVER (-4)       /* a CUDA driver call failed (reference: CU_CALL_RET, cuda_common.hpp:42-61) */
+#define FLMIP_ERR_OUT_OF_MEMORY (-5)
+
+/* flags of flmip_image_create */
+#define FLMIP_IMAGE_NO_DOUBLE 1u     /* FLOOR_DEVICE_NO_DOUBLE encoders for 16-bit normalized formats (host_image.hpp:398-402) */
+#define FLMIP_IMAGE_FORCE_GENERIC 2u /* never use the single-pass kernel (validation / A-B timing) */
+
+typedef struct flmip_image_s* flmip_image;
+typedef void* flmip_stream; /* CUstream */
+typedef void* flmip_event;  /* CUevent */
+
+typedef struct flmip_device_info {
+	char name[128];
+	uint64_t global_mem_size;
+	uint32_t sm_major, sm_minor;
+	uint32_t units;                 /* SM count                     (fl::device::units) */
+	uint32_t max_total_local_size;  /* max threads per block        (fl::device::max_total_local_size) */
+	uint32_t max_image_2d_dim[2], max_image_3d_dim[3];
+	uint32_t max_mip_levels;
+	uint32_t driver_version;
+} flmip_device_info;
+
+typedef struct flmip_level_info {
+	uint32_t dim[3];      /* texels, unused dims 0; a level with a zero dim is empty (image_types.hpp:751-766) */
+	uint64_t offset;      /* byte offset of the level in the level-major image */
+	uint64_t size;        /* bytes of the level over all layers */
+	uint64_t slice_size;  /* bytes of one layer */
+} flmip_level_info;
+
+/* -- bring-up: replaces cuda_api_init + the cuda_context ctor's device enumeration
+ *    (src/device/cuda/cuda_api.cpp:53-, src/device/cuda/cuda_context.cpp:40-415) ------------------------ */
+int flmip_init(void);
+int flmip_device_count(void);
+int flmip_get_device_info(int device, flmip_device_info* out);
+const char* flmip_last_error_string(void);
+/* number of kernels this library launched since load (bench bookkeeping) */
+uint64_t flmip_launch_count(void);
+
+/* -- queues: cuda_context::create_queue / cuda_queue::finish (cuda_context.cpp:418-437, cuda_queue.cpp:26-72) */
+int flmip_stream_create(int device, flmip_stream* out);
+int flmip_stream_destroy(int device, flmip_stream stream);
+int flmip_stream_sync(int device, flmip_stream stream);
+/* profiling: cuda_queue::start_profiling / stop_profiling (cuda_queue.cpp:58-70) */
+int flmip_event_create(int device, flmip_event* out);
+int flmip_event_record(int device, flmip_event ev, flmip_stream stream);
+int flmip_event_sync(int device, flmip_event ev);
+int flmip_event_elapsed_ms(int device, flmip_event start, flmip_event stop, float* ms);
+int flmip_event_destroy(int device, flmip_event ev);
+/* page-locked host staging buffers */
+int flmip_host_alloc(int device, size_t size, void** out);
+int flmip_host_free(int device, void* ptr);
+
+/* -- images: cuda_image::create_internal (src/device/cuda/cuda_image.cpp:158-539), but as ONE linear
+ *    allocation in floor's host layout (level-major, layers contiguous per level, tight rows:
+ *    device_image.hpp:594-615, host_image.cpp:81-88) with 64-bit offsets.
+ *    image_dim = (w, h, d or layers, layers-for-3D); cube: 6 faces per layer (image_types.hpp:716-726). */
+int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags,
+					   flmip_image* out);
+int flmip_image_destroy(flmip_image img);
+int flmip_image_mip_level_count(flmip_image img, uint32_t* out);
+int flmip_image_layer_count(flmip_image img, uint32_t* out);
+int flmip_image_data_size(flmip_image img, uint64_t* out);          /* all levels */
+int flmip_image_get_level_info(flmip_image img, uint32_t level, flmip_level_info* out);
+int flmip_image_device_ptr(flmip_image img, uint64_t* out);         /* CUdeviceptr of level 0 */
+/* 1 if generate uses the single-pass kernel; *fast_levels = number of levels (incl. level 0) it covers */
+int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast_levels, uint32_t* launches);
+
+/* -- host <-> device: cuda_image::write / map / unmap copies (cuda_image.cpp:588-813).
+ *    Whole levels [level_first, level_last] (inclusive, like mip_level_range) in host layout; async on `stream`. */
+int flmip_image_upload(flmip_image img, const void* src, size_t src_size, uint32_t level_first, uint32_t level_last, flmip_stream stream);
+int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, flmip_stream stream);
+/* sub-region write with floor's semantics (offset / extent in level-0 texels, inclusive level and layer ranges,
+ * source tightly packed per level): cuda_image::write, cuda_image.cpp:588-673 */
+int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
+					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream);
+int flmip_image_zero(flmip_image img, flmip_stream stream);          /* cuda_image::zero, cuda_image.cpp:675-701 */
+
+/* -- THE hot path: device_image::generate_mip_map_chain (src/device/device_image.cpp:235-328) + the
+ *    libfloor_mip_map_minify_* kernels (include/floor/device/backend/mip_map_minify.hpp:89-126).
+ *    Enqueues on `stream` and returns; the C++ drop-in adds the blocking flmip_stream_sync the reference
+ *    implies (wait_until_completion = true, device_image.cpp:322). */
+int flmip_mip_chain_generate(flmip_image img, flmip_stream stream);
+/* regenerate only levels > first_level (dirty-level update); first_level = 0 is the full chain */
+int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream);
+
+/* -- bench / validation helper: fill level 0 with the counter-based synthetic pattern of SURVEY.md 8d
+ *    (same definition as flo_fill_synthetic of the oracle); global layer ids start at layer_id0 */
+int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
