@@ -228,15 +228,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-		"{\n\t"
-		".reg .pred p;\n\t"
-		"WAIT_LOOP:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra WAIT_DONE;\n\t"
-		"bra WAIT_LOOP;\n\t"
-		"WAIT_DONE:\n\t"
-		"}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+	// try_wait suspends in hardware for a bounded time; the trip counter turns a lost TMA transaction (bad descriptor)
+	// into a trap instead of a hung GPU
+	for (uint32_t spins = 0;; ++spins) {
+		uint32_t done;
+		asm volatile(
+			"{\n\t"
+			".reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t"
+			"}"
+			: "=r"(done)
+			: "r"(smem_u32(bar)), "r"(parity)
+			: "memory");
+		if (done) return;
+		if (spins > (1u << 24)) __trap();
+	}
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -618,7 +625,7 @@ extern "C" __global__ void __launch_bounds__(256) flmip_generic(const __grid_con
 	}
 }
 
-// same definition as flo_synth_element() of the oracle
+// counter-based pattern of SURVEY.md 8d (the CPU checker defines the same function)
 extern "C" __global__ void __launch_bounds__(256) flmip_fill(const __grid_constant__ flmip_fill_params P) {
 	const uint64_t total = P.elems_per_layer * P.layers;
 	const uint32_t ek = P.elem_kind;

@@ -111,7 +111,7 @@ int flmip_mip_chain_generate(flmip_image img, flmip_stream stream);
 int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream);
 
 /* -- bench / validation helper: fill level 0 with the counter-based synthetic pattern of SURVEY.md 8d
- *    (same definition as flo_fill_synthetic of the oracle); global layer ids start at layer_id0 */
+ *    (the CPU checker defines the same pattern); global layer ids start at layer_id0 */
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream);
 
 #ifdef __cplusplus

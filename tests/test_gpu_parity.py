@@ -1,0 +1,237 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI library; the oracle
+is only the checker.  Bit-exact for every format (stricter than the <= 1 ulp the north star allows for fp16/fp32:
+the kernels evaluate the same IEEE operations in the same order)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import floor_b200
+from floor_b200.image_types import IMAGE_TYPE as T, MEMORY_FLAG as MF
+from floor_b200 import image_types as it
+
+pytestmark = pytest.mark.gpu
+M = T.FLAG_MIPMAPPED | T.READ_WRITE
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FLOAT_ULP_TOLERANCE = 0  # north star allows 1 ulp for fp16 / fp32; we require 0
+
+
+def gpu_chain(gpu_ctx, l0, dim, t, **kw):
+    ctx, dev, q = gpu_ctx
+    img = ctx.create_image(q, dim, t, flags=MF.READ_WRITE | MF.HOST_READ_WRITE, **kw)
+    img.upload_levels(q, l0, 0, 0)
+    img.generate_mip_map_chain(q)
+    out = img.download_levels(q)
+    plan = img.plan()
+    img.destroy()
+    return out, plan
+
+
+def assert_same(a, b, t, dim, what=""):
+    assert a.size == b.size, (hex(t), dim, a.size, b.size)
+    if not np.array_equal(a, b):
+        bad = np.nonzero(a != b)[0]
+        raise AssertionError(f"{what} type={t:#x} dim={dim}: {bad.size} differing bytes, first at {int(bad[0])} "
+                             f"(gpu={int(a[bad[0]])} oracle={int(b[bad[0]])})")
+
+
+ALL_FORMATS = [T.R8, T.RG8, T.RGBA8, T.R16, T.RG16, T.RGBA16, T.R8I_NORM, T.RG8I_NORM, T.RGBA8I_NORM, T.R16I_NORM, T.RG16I_NORM,
+               T.RGBA16I_NORM, T.R8UI, T.RG8UI, T.RGBA8UI, T.R8I, T.RG8I, T.RGBA8I, T.R16UI, T.RG16UI, T.RGBA16UI, T.R16I, T.RG16I,
+               T.RGBA16I, T.R32UI, T.RG32UI, T.RGBA32UI, T.R32I, T.RG32I, T.RGBA32I, T.R16F, T.RG16F, T.RGBA16F, T.R32F, T.RG32F,
+               T.RGBA32F]
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_single_pass_2d_all_formats(gpu_ctx, oracle_mod, fmt):
+    """power-of-two 2D images large enough for the TMA single-pass kernel (several tiles, groups and the layer stage)"""
+    bpp = it.bytes_per_pixel(fmt)
+    w = max(2 * 512 // bpp, 256)
+    for dim in [(w, 256), (w * 2, 128), (512 // bpp, 64)]:
+        t = T.IMAGE_2D | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 100 + (fmt & 0xFFFF))
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["single_pass"], (hex(t), dim, plan)
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "single-pass 2D")
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_single_pass_3d_all_formats(gpu_ctx, oracle_mod, fmt):
+    bpp = it.bytes_per_pixel(fmt)
+    for dim in [(2 * 128 // bpp if bpp < 16 else 32, 32, 32), (128 // bpp if bpp < 16 else 8, 16, 64)]:
+        t = T.IMAGE_3D | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 200 + (fmt & 0xFFFF))
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["single_pass"], (hex(t), dim, plan)
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "single-pass 3D")
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_general_path_all_formats(gpu_ctx, oracle_mod, fmt):
+    """NPOT / small / 1D images take the general per-level kernel"""
+    for base, dim in [(T.IMAGE_2D, (37, 21)), (T.IMAGE_2D, (100, 60)), (T.IMAGE_2D_ARRAY, (20, 12, 3)), (T.IMAGE_3D, (12, 10, 6)),
+                      (T.IMAGE_1D, (33,)), (T.IMAGE_1D_ARRAY, (64, 2)), (T.IMAGE_2D, (16, 16))]:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 300 + (fmt & 0xFFFF))
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert not plan["single_pass"]
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4), t, dim, "general")
+
+
+def test_general_equals_single_pass(gpu_ctx, oracle_mod):
+    """the POT fast form is a derived identity of the general sampler: both GPU paths must agree"""
+    for base, fmt, dim in [(T.IMAGE_2D, T.RGBA16F, (512, 512)), (T.IMAGE_2D_ARRAY, T.RGBA8, (256, 128, 5)), (T.IMAGE_3D, T.R32F, (64, 64, 64)),
+                           (T.IMAGE_2D, T.RGBA32UI, (128, 128)), (T.IMAGE_2D, T.RGBA16, (256, 256))]:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 7)
+        a, pa = gpu_chain(gpu_ctx, l0, dim, t)
+        b, pb = gpu_chain(gpu_ctx, l0, dim, t, force_generic=True)
+        assert pa["single_pass"] and not pb["single_pass"]
+        assert_same(a, b, t, dim, "single-pass vs general")
+
+
+def test_layered_and_cube(gpu_ctx, oracle_mod):
+    cases = [(T.IMAGE_2D_ARRAY | T.RGBA8, (256, 256, 7)), (T.IMAGE_2D_ARRAY | T.RGBA8, (1024, 1024, 3)), (T.IMAGE_CUBE | T.RGBA32F, (128, 128)),
+             (T.IMAGE_CUBE_ARRAY | T.RGBA32F, (64, 64, 3)), (T.IMAGE_CUBE_ARRAY | T.RGBA16F, (256, 256, 2)), (T.IMAGE_DEPTH_ARRAY | T.FORMAT_32 | T.FLOAT, (256, 128, 4))]
+    for bt, dim in cases:
+        t = bt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 11)
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["single_pass"] and plan["launches"] == 1, plan
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "layered")
+
+
+def test_non_square_and_level_limit(gpu_ctx, oracle_mod):
+    for dim in [(2048, 64), (64, 2048), (4096, 256), (128, 1024)]:
+        t = T.IMAGE_2D | T.RGBA16F | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 13)
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["single_pass"]
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "non-square")
+    for limit in [2, 3, 5, 8]:
+        dim, t = (1024, 1024), T.IMAGE_2D | T.RGBA8 | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 14)
+        got, _ = gpu_chain(gpu_ctx, l0, dim, t, mip_level_limit=limit)
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, mip_level_limit=limit, threads=8), t, dim, f"limit {limit}")
+    for dim in [(128, 16, 16), (32, 16, 256), (64, 128, 32)]:
+        t = T.IMAGE_3D | T.R32F | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 15)
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["single_pass"]
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "non-cubic")
+
+
+def test_no_double_variant(gpu_ctx, oracle_mod):
+    for fmt in [T.RGBA16, T.RG16I_NORM]:
+        dim, t = (256, 256), T.IMAGE_2D | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 16)
+        a, _ = gpu_chain(gpu_ctx, l0, dim, t, no_double=True)
+        assert_same(a, oracle_mod.generate_mip_map_chain(l0, dim, t, no_double=True, threads=8), t, dim, "no-double")
+        b, _ = gpu_chain(gpu_ctx, l0, dim, t)
+        assert not np.array_equal(a, b)  # the two encoder modes do differ
+
+
+def test_adversarial_floats(gpu_ctx, oracle_mod):
+    """+-0, subnormals, +-65504 and 1-ulp neighbours (fp16); mixed exponents / cancellation and subnormals (fp32)"""
+    rng = np.random.default_rng(3)
+    dim = (256, 256)
+    h = rng.integers(0, 0x7C00, size=dim[0] * dim[1] * 4, dtype=np.uint16) | (rng.integers(0, 2, size=dim[0] * dim[1] * 4, dtype=np.uint16) << 15)
+    special = np.array([0x0000, 0x8000, 0x0001, 0x8001, 0x03FF, 0x0400, 0x7BFF, 0xFBFF, 0x7BFE, 0x3C00, 0x3C01, 0xBC00], np.uint16)
+    h[:: 5] = special[rng.integers(0, special.size, size=h[::5].size)]
+    t = T.IMAGE_2D | T.RGBA16F | M
+    got, _ = gpu_chain(gpu_ctx, h, dim, t)
+    assert_same(got, oracle_mod.generate_mip_map_chain(h, dim, t, threads=8), t, dim, "adversarial fp16")
+    e = rng.integers(1, 254, size=dim[0] * dim[1] * 4, dtype=np.uint32)
+    f = (rng.integers(0, 2, size=e.size, dtype=np.uint32) << 31) | (e << 23) | rng.integers(0, 1 << 23, size=e.size, dtype=np.uint32)
+    f[::7] = rng.integers(0, 1 << 23, size=f[::7].size, dtype=np.uint32)  # subnormals
+    f[::11] = np.uint32(0x80000000)
+    t = T.IMAGE_2D | T.RGBA32F | M
+    got, _ = gpu_chain(gpu_ctx, f, dim, t)
+    assert_same(got, oracle_mod.generate_mip_map_chain(f, dim, t, threads=8), t, dim, "adversarial fp32")
+
+
+def test_golden_fixtures_on_gpu(gpu_ctx, oracle_mod):
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        cases = json.load(f)
+    small = np.load(os.path.join(GOLDEN, "golden_small.npz"))
+    for c in cases:
+        dim, t = tuple(c["dim"]), int(c["type"], 16)
+        if it.channel_count(t) == 3:
+            continue
+        l0 = oracle_mod.fill_synthetic(dim, t, c["config_id"])
+        got, _ = gpu_chain(gpu_ctx, l0, dim, t, no_double=c["no_double"])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == c["chain_sha256"], c["name"]
+        if c["name"] in small.files:
+            assert np.array_equal(got, small[c["name"]])
+
+
+def test_device_fill_matches_oracle_fill(gpu_ctx, oracle_mod):
+    ctx, dev, q = gpu_ctx
+    for bt, dim in [(T.IMAGE_2D | T.RGBA16F, (128, 64)), (T.IMAGE_2D_ARRAY | T.RGBA8, (64, 64, 5)), (T.IMAGE_3D | T.R32F, (32, 16, 8)),
+                    (T.IMAGE_2D | T.RG32I, (64, 64)), (T.IMAGE_2D | T.R16, (64, 64))]:
+        t = bt | M
+        img = ctx.create_image(q, dim, t)
+        img.fill_synthetic(q, 42, layer_id0=3)
+        got = img.download_levels(q, 0, 0)
+        want = oracle_mod.fill_synthetic(dim, t, 42, layer_id0=3)
+        assert np.array_equal(got, want), hex(t)
+        img.destroy()
+
+
+def test_relaunch_is_idempotent_and_counters_reset(gpu_ctx, oracle_mod):
+    ctx, dev, q = gpu_ctx
+    dim, t = (2048, 2048), T.IMAGE_2D | T.RGBA16F | M
+    img = ctx.create_image(q, dim, t)
+    img.fill_synthetic(q, 2)
+    outs = []
+    for _ in range(3):
+        img.generate_mip_map_chain(q)
+        outs.append(hashlib.sha256(img.download_levels(q).tobytes()).hexdigest())
+    assert outs[0] == outs[1] == outs[2]
+    l0 = oracle_mod.fill_synthetic(dim, t, 2)
+    assert hashlib.sha256(oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8).tobytes()).hexdigest() == outs[0]
+    img.destroy()
+
+
+def test_unsupported_types_are_rejected(gpu_ctx):
+    ctx, dev, q = gpu_ctx
+    for t, dim in [(T.IMAGE_2D | T.RGB8 | M, (64, 64)), (T.IMAGE_2D | T.FORMAT_64 | T.FLOAT | T.CHANNELS_1 | M, (64, 64)),
+                   (T.IMAGE_2D | T.FLAG_MSAA | T.RGBA8 | M, (64, 64)), (T.IMAGE_CUBE | T.RGBA8 | M, (64, 32))]:
+        with pytest.raises(floor_b200.FlmipError):
+            ctx.create_image(q, dim, t)
+
+
+def test_generate_mip_maps_life_cycle(gpu_ctx, oracle_mod):
+    """ctor upload -> chain, write() -> chain, map()/unmap() -> chain (cuda_image.cpp:533-536, 667-670, 803-806)"""
+    ctx, dev, q = gpu_ctx
+    dim, t = (512, 256), T.IMAGE_2D | T.RGBA8 | T.FLAG_MIPMAPPED | T.READ
+    l0 = oracle_mod.fill_synthetic(dim, t, 21)
+    img = ctx.create_image(q, dim, t, data=l0, flags=MF.READ | MF.HOST_READ_WRITE | MF.GENERATE_MIP_MAPS)
+    assert img.get_generate_mip_maps() and img.get_image_data_size() == l0.size  # level 0 only (device_image.hpp:486)
+    want = oracle_mod.generate_mip_map_chain(l0, dim, t | T.WRITE, threads=4)
+    assert np.array_equal(img.download_levels(q), want)
+    l0b = oracle_mod.fill_synthetic(dim, t, 22)
+    assert img.write(q, l0b, (0, 0, 0), (dim[0], dim[1], 1), (0, 0), (0, 0))
+    assert np.array_equal(img.download_levels(q), oracle_mod.generate_mip_map_chain(l0b, dim, t | T.WRITE, threads=4))
+    m = img.map(q)
+    assert m.size == l0.size and np.array_equal(m, l0b)
+    m[:] = l0
+    assert img.unmap(q, m)
+    assert np.array_equal(img.download_levels(q), want)
+    assert not img.write(q, l0, (0, 0, 0), (dim[0] + 1, dim[1], 1), (0, 0), (0, 0))  # write_check failure -> False
+    img.destroy()
+
+
+def test_partial_write_then_regenerate(gpu_ctx, oracle_mod):
+    ctx, dev, q = gpu_ctx
+    dim, t = (256, 256, 3), T.IMAGE_2D_ARRAY | T.RGBA8 | M
+    l0 = oracle_mod.fill_synthetic(dim, t, 31).copy()
+    img = ctx.create_image(q, dim, t, data=np.concatenate([l0, np.zeros(oracle_mod.image_data_size(dim, t) - l0.size, np.uint8)]))
+    patch = np.arange(64 * 32 * 4, dtype=np.uint32).astype(np.uint8)
+    assert img.write(q, patch, (16, 8, 0), (64, 32, 1), (0, 0), (1, 1))
+    img.generate_mip_map_chain(q)
+    ref0 = l0.reshape(3, 256, 256, 4).copy()
+    ref0[1, 8:40, 16:80, :] = patch.reshape(32, 64, 4)
+    assert np.array_equal(img.download_levels(q), oracle_mod.generate_mip_map_chain(ref0, dim, t, threads=4))
+    img.destroy()
