@@ -132,7 +132,7 @@ def run_ours(args, rank, world, local_rank):
     rdim = list(dim)
     if sharded:
         is_cube = bool(t & T.FLAG_CUBE)
-        total_layers = dim[2]
+        total_layers = args.layers or dim[2]
         lo, n = shard_layers(total_layers, world, rank)
         rdim[2] = n
         layer_id0 = lo * (6 if is_cube else 1)
@@ -182,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API with host buffers (pinned), H2D + chain + D2H every step ----
     e2e_steps = max(2, min(args.steps, 5))
-    if level0 > (4 << 30):
+    if level0 > (4 << 30) or args.no_e2e:
         e2e_steps = 0  # layered multi-GB shards: no host staging buffer of that size; e2e is reported for the default workload
     h2d = level0
     d2h = alg_bytes - level0
@@ -308,6 +308,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=0, help="tuning runs only: override the layer / cube count of c3 / c4")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

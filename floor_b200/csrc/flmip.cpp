@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -67,6 +68,7 @@ struct device_state {
 	std::mutex mtx;
 	std::unordered_map<std::string, CUfunction> functions;
 	flmip_device_info info {};
+	uint32_t smem_per_sm = 0, smem_per_block_optin = 0;
 };
 
 std::once_flag init_once;
@@ -142,6 +144,8 @@ void do_init() {
 		ds->info.max_image_3d_dim[1] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE3D_HEIGHT);
 		ds->info.max_image_3d_dim[2] = attr(CU_DEVICE_ATTRIBUTE_MAXIMUM_TEXTURE3D_DEPTH);
 		ds->info.max_mip_levels = FLMIP_MAX_LEVELS;
+		ds->smem_per_sm = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_MULTIPROCESSOR);
+		ds->smem_per_block_optin = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN);
 		ds->info.driver_version = (uint32_t)version;
 		devices.push_back(ds);
 	}
@@ -256,6 +260,7 @@ struct flmip_image_s {
 	uint32_t fast_level_count = 0; // levels [0, fast_level_count) are produced by the single-pass launch
 	flmip_fast_params fast_params {};
 	flmip_tiling_rt tiling {};
+	uint32_t fast_smem = 0, fast_grid = 0; // dynamic shared memory and persistent grid of the single-pass launch
 	alignas(64) CUtensorMap tmap {};
 	std::string fast_name;
 };
@@ -347,18 +352,37 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	for (uint32_t l = 0; l < FLMIP_MAX_LEVELS; ++l) P.level_off[l] = l < im.level_count ? im.levels[l].offset : 0;
 	P.dim[0] = W; P.dim[1] = H; P.dim[2] = D;
 	P.tiles[0] = W / tl.tx; P.tiles[1] = H / tl.ty; P.tiles[2] = D / tl.tz;
-	for (int i = 0; i < 3; ++i) P.groups[i] = (P.tiles[i] + tl.group - 1) / tl.group;
+	// units of 2 x 2 (x 2) tiles when every dim has at least two tiles
+	P.unit_shift = (P.tiles[0] >= 2 && P.tiles[1] >= 2 && (!is3d || P.tiles[2] >= 2)) ? 1u : 0u;
+	for (int i = 0; i < 3; ++i) {
+		P.units[i] = (i == 2 && !is3d) ? 1u : P.tiles[i] >> P.unit_shift;
+		P.unit_cshift[i] = (uint32_t)flmip_ilog2(P.units[i]);
+		P.groups[i] = (P.units[i] + tl.group - 1) / tl.group;
+	}
+	const uint64_t total_tiles = (uint64_t)P.tiles[0] * P.tiles[1] * P.tiles[2] * im.layers;
+	if (total_tiles > 0x7FFFFFFFull) return FLMIP_OK; // general path
+	P.total_units = (uint32_t)(total_tiles >> (P.unit_shift * im.dc));
 	P.layers = im.layers;
 	P.no_double = im.no_double;
 
 	// tile stage
 	uint32_t lvl = simulate_cascade(tl.tx, tl.ty, tl.tz, is3d, 0, im.level_count);
 	uint32_t covered = lvl;
-	if (next_level_has_texels(im, lvl)) {
+	uint32_t rw = tl.tx >> lvl, rh = tl.ty >> lvl, rd = tl.tz >> lvl; // remainder of one tile, then of one unit
+	bool more = next_level_has_texels(im, lvl);
+	if (more && P.unit_shift) {
+		// unit stage
+		rw *= 2u; rh *= 2u; if (is3d) rd *= 2u;
+		const uint32_t l2 = simulate_cascade(rw, rh, rd, is3d, lvl, im.level_count);
+		rw >>= (l2 - lvl); rh >>= (l2 - lvl); if (is3d) rd >>= (l2 - lvl);
+		covered = lvl = l2;
+		more = next_level_has_texels(im, lvl);
+	}
+	if (more) {
 		// group stage
-		const uint32_t ntx = P.tiles[0] < tl.group ? P.tiles[0] : tl.group, nty = P.tiles[1] < tl.group ? P.tiles[1] : tl.group,
-					   ntz = P.tiles[2] < tl.group ? P.tiles[2] : tl.group;
-		lvl = simulate_cascade((tl.tx >> lvl) * ntx, (tl.ty >> lvl) * nty, (tl.tz >> lvl) * ntz, is3d, lvl, im.level_count);
+		const uint32_t ntx = P.units[0] < tl.group ? P.units[0] : tl.group, nty = P.units[1] < tl.group ? P.units[1] : tl.group,
+					   ntz = P.units[2] < tl.group ? P.units[2] : tl.group;
+		lvl = simulate_cascade(rw * ntx, rh * nty, rd * ntz, is3d, lvl, im.level_count);
 		covered = lvl;
 		if (next_level_has_texels(im, lvl)) {
 			// layer stage: the whole level must fit into the cascade scratch, else the general path finishes the chain
@@ -371,11 +395,16 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	im.tiling = tl;
 
 	// counters: one per tile group and one per layer, zeroed once; the kernel resets what it uses
-	const uint64_t n_counters = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2] + im.layers;
+	const uint64_t n_groups = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2];
+	const uint64_t n_column_words = n_groups * tl.group * FLMIP_COLUMN_COUNTER_STRIDE;
+	const uint64_t n_counters = n_groups + im.layers + 1000000u /* debug */ + n_column_words;
 	CU_TRY(cu.p_cuMemAlloc(&im.counters, n_counters * sizeof(uint32_t)), "cuMemAlloc(counters)");
 	CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, nullptr), "cuMemsetD32Async(counters)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
 	P.counters = im.counters;
+	P.sched = im.counters + (n_groups + im.layers + 2u) * sizeof(uint32_t);
+	P.debug_off = (uint32_t)((n_groups + im.layers + 8u) / 2u);
+	P.column_counters = im.counters + (n_groups + im.layers + 1000000u) * sizeof(uint32_t);
 
 	// TMA descriptor over level 0: rank 3 in uint32 units -- (x, y, layer) for 2D / array / cube, (x, y, z) for volumes
 	const cuuint64_t row_bytes = (cuuint64_t)W * im.bpp;
@@ -388,11 +417,33 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 									   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
 		   "cuTensorMapEncodeTiled");
 
+	// persistent launch shape: CTAs per SM x ring depth that fit the SM's shared memory (1 KiB is reserved per CTA).
+	// Defaults: 2 CTAs per SM, as many stages as fit (at most 4); FLMIP_CTAS_PER_SM / FLMIP_STAGES override for tuning.
+	auto env_u32 = [](const char* name, uint32_t def) {
+		const char* v = getenv(name);
+		return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : def;
+	};
+	uint32_t ctas_per_sm = env_u32("FLMIP_CTAS_PER_SM", 2);
+	if (ctas_per_sm < 1) ctas_per_sm = 1;
+	const uint32_t per_cta = ds->smem_per_sm / ctas_per_sm - 1024u - 2048u /* static: mbarriers, ticket, lock, unit patches */;
+	const uint32_t budget = per_cta < ds->smem_per_block_optin - 2048u ? per_cta : ds->smem_per_block_optin - 2048u;
+	if (budget < tl.cascade_smem_bytes + tl.tile_bytes) return fail(FLMIP_ERR_INVALID, "FLMIP_CTAS_PER_SM=%u leaves no room for a tile", ctas_per_sm);
+	uint32_t stages = (budget - tl.cascade_smem_bytes) / tl.tile_bytes;
+	const uint32_t want = env_u32("FLMIP_STAGES", 4);
+	if (stages > want) stages = want;
+	if (stages > FLMIP_MAX_STAGES) stages = FLMIP_MAX_STAGES;
+	if (stages < 1) stages = 1;
+	P.stages = stages;
+	P.debug_flags = env_u32("FLMIP_DEBUG_FLAGS", 0);
+	im.fast_smem = stages * tl.tile_bytes + tl.cascade_smem_bytes;
+	const uint64_t resident = (uint64_t)ds->info.units * ctas_per_sm;
+	im.fast_grid = (uint32_t)(P.total_units < resident ? P.total_units : resident);
+
 	char name[64];
 	snprintf(name, sizeof(name), "flmip_fast%ud_k%u_c%u", im.dc, im.elem_kind, im.channels);
 	im.fast_name = name;
 	CUfunction fn = nullptr;
-	const int rc = get_function(ds, im.fast_name, tl.smem_bytes, &fn); // resolve now: fail at creation, not at first use
+	const int rc = get_function(ds, im.fast_name, im.fast_smem, &fn); // resolve now: fail at creation, not at first use
 	if (rc != FLMIP_OK) return rc;
 	im.fast = true;
 	return FLMIP_OK;
@@ -719,12 +770,11 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 	uint32_t next = first_level + 1; // first level still to be produced
 	if (img->fast && first_level == 0) {
 		CUfunction fn = nullptr;
-		int rc = get_function(ds, img->fast_name, img->tiling.smem_bytes, &fn);
+		int rc = get_function(ds, img->fast_name, img->fast_smem, &fn);
 		if (rc != FLMIP_OK) return rc;
 		const flmip_fast_params& P = img->fast_params;
 		void* args[] = { &img->tmap, const_cast<flmip_fast_params*>(&P) };
-		const uint64_t grid = (uint64_t)P.tiles[0] * P.tiles[1] * P.tiles[2] * img->layers;
-		rc = launch(fn, grid, 256, img->tiling.smem_bytes, (CUstream)stream, args);
+		rc = launch(fn, img->fast_grid, FLMIP_BLOCK_THREADS, img->fast_smem, (CUstream)stream, args);
 		if (rc != FLMIP_OK) return rc;
 		next = img->fast_level_count;
 	}
@@ -736,6 +786,13 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 	return FLMIP_OK;
 }
 
+int flmip_debug_read(flmip_image img, uint64_t* out, uint32_t n) {
+	WITH_DEVICE(img->device)
+	cu.p_cuStreamSynchronize(nullptr);
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, img->counters + (uint64_t)img->fast_params.debug_off * 8u, n * 8u, nullptr), "dbg");
+	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "dbg");
+	return 0;
+}
 int flmip_mip_chain_generate(flmip_image img, flmip_stream stream) { return flmip_mip_chain_generate_from(img, 0, stream); }
 
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {

@@ -20,6 +20,18 @@
 
 namespace {
 
+template <int BYTES> __device__ __forceinline__ uint32_t get_elem(const uint32_t* w, int i) {
+	if constexpr (BYTES == 4) return w[i];
+	else if constexpr (BYTES == 2) return (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+	else return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+}
+template <int BYTES> __device__ __forceinline__ void put_elem(uint32_t* w, int i, uint32_t raw) {
+	if constexpr (BYTES == 4) w[i] = raw;
+	else if constexpr (BYTES == 2) w[i >> 1] |= raw << (16 * (i & 1));
+	else w[i >> 2] |= raw << (8 * (i & 3));
+}
+
+
 // ------------------------------------------------------------------------------------------------------
 // element codecs
 // ------------------------------------------------------------------------------------------------------
@@ -29,6 +41,14 @@ template <uint32_t EK> struct Codec {
 	static constexpr int BYTES = flmip_elem_bytes(EK);
 	static constexpr uint32_t MASK = (BYTES == 4 ? 0xFFFFFFFFu : (BYTES == 2 ? 0xFFFFu : 0xFFu));
 
+	// Conversions that stay off the quarter-rate XU pipe (I2F / F2I / F2F): an unsigned integer u < 2^23 placed in the
+	// mantissa of 2^23 is the float 2^23 + u, so  float(u) * c == fma(2^23 + u, c, -(2^23 * c))  exactly (2^23 * c is a
+	// power-of-two scaling of c, the fused product-sum is rounded once), and for 0 <= t < 2^23 the low mantissa bits
+	// of  t + 2^23  rounded toward zero are trunc(t).
+	static constexpr float MAGIC = 8388608.0f; // 2^23 == 0x4B000000
+	static constexpr float UNORM_C = (EK == FLMIP_EK_UNORM8 ? (float)(1.0 / 255.0) : (float)(1.0 / 65535.0));
+	static constexpr float UNORM_S = (EK == FLMIP_EK_UNORM8 ? 255.0f : 65535.0f);
+
 	// decode zero-extended storage bits into the compute domain (fp32 bits or widened 32-bit integer)
 	// host_image.hpp:487-561 (float / normalized), :640-667 (int / uint)
 	static __device__ __forceinline__ uint32_t dec(uint32_t raw) {
@@ -36,18 +56,34 @@ template <uint32_t EK> struct Codec {
 			return raw;
 		} else if constexpr (EK == FLMIP_EK_F16) {
 			return __float_as_uint(__half2float(__ushort_as_half((unsigned short)raw)));
-		} else if constexpr (EK == FLMIP_EK_UNORM8) {
-			return __float_as_uint(__fmul_rn(__uint2float_rn(raw), (float)(1.0 / 255.0)));
+		} else if constexpr (EK == FLMIP_EK_UNORM8 || EK == FLMIP_EK_UNORM16) {
+			// == __fmul_rn(__uint2float_rn(raw), UNORM_C)
+			return __float_as_uint(__fmaf_rn(__uint_as_float(0x4B000000u | raw), UNORM_C, -(MAGIC * UNORM_C)));
 		} else if constexpr (EK == FLMIP_EK_SNORM8) {
 			return __float_as_uint(__fmul_rn(__int2float_rn((int)(signed char)raw), (float)(1.0 / 127.0)));
-		} else if constexpr (EK == FLMIP_EK_UNORM16) {
-			return __float_as_uint(__fmul_rn(__uint2float_rn(raw), (float)(1.0 / 65535.0)));
 		} else if constexpr (EK == FLMIP_EK_SNORM16) {
 			return __float_as_uint(__fmul_rn(__int2float_rn((int)(short)raw), (float)(1.0 / 32767.0)));
 		} else if constexpr (EK == FLMIP_EK_I8) {
 			return (uint32_t)(int)(signed char)raw;
 		} else { // I16
 			return (uint32_t)(int)(short)raw;
+		}
+	}
+
+	// decode element i of a row of packed 32-bit words
+	static __device__ __forceinline__ uint32_t dec_at(const uint32_t* w, int i) {
+		if constexpr (EK == FLMIP_EK_UNORM8) {
+			// one PRMT builds 0x4B0000uu
+			return __float_as_uint(__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7440u | (uint32_t)(i & 3))), UNORM_C,
+											 -(MAGIC * UNORM_C)));
+		} else if constexpr (EK == FLMIP_EK_UNORM16) {
+			return __float_as_uint(
+				__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 1], 0x4B000000u, (i & 1) ? 0x7432u : 0x7410u)), UNORM_C, -(MAGIC * UNORM_C)));
+		} else if constexpr (EK == FLMIP_EK_F16) {
+			const __half2 h = *reinterpret_cast<const __half2*>(&w[i >> 1]);
+			return __float_as_uint((i & 1) ? __high2float(h) : __low2float(h));
+		} else {
+			return dec(get_elem<BYTES>(w, i));
 		}
 	}
 
@@ -60,16 +96,46 @@ template <uint32_t EK> struct Codec {
 		} else if constexpr (EK == FLMIP_EK_F16) {
 			return (uint32_t)__half_as_ushort(__float2half_rn(__uint_as_float(v)));
 		} else if constexpr (EK == FLMIP_EK_UNORM8) {
-			return (uint32_t)__float2int_rz(__fmul_rn(__uint_as_float(v), 255.0f)) & 0xFFu;
+			// v in [0, 1] -> t in [0, 255]: trunc(t) sits in the low mantissa byte of t + 2^23 (RZ)
+			return __float_as_uint(__fadd_rz(__fmul_rn(__uint_as_float(v), 255.0f), MAGIC)) & 0xFFu;
 		} else if constexpr (EK == FLMIP_EK_SNORM8) {
 			return (uint32_t)__float2int_rz(__fmul_rn(__uint_as_float(v), 127.0f)) & 0xFFu;
 		} else {
-			// 9..16 bit normalized: fp_scale_type is double unless FLOOR_DEVICE_NO_DOUBLE (host_image.hpp:398-402)
-			constexpr float scale_f = (EK == FLMIP_EK_UNORM16 ? 65535.0f : 32767.0f);
-			constexpr double scale_d = (EK == FLMIP_EK_UNORM16 ? 65535.0 : 32767.0);
+			// 9..16 bit normalized: fp_scale_type is double unless FLOOR_DEVICE_NO_DOUBLE (host_image.hpp:398-402).
+			// double(f) * scale is exact (24 + 16 significant bits), so the reference computes trunc(f * scale) of the
+			// EXACT product; the fp32 product rounded toward zero has the same integer part (an integer n <= exact
+			// is itself a float, hence <= RZ(exact)).  The all-float variant truncates the RN product instead.
+			constexpr float scale = (EK == FLMIP_EK_UNORM16 ? 65535.0f : 32767.0f);
 			const float f = __uint_as_float(v);
-			const int q = no_double ? __float2int_rz(__fmul_rn(f, scale_f)) : __double2int_rz(__dmul_rn((double)f, scale_d));
-			return (uint32_t)q & 0xFFFFu;
+			const float t = no_double ? __fmul_rn(f, scale) : __fmul_rz(f, scale);
+			if constexpr (EK == FLMIP_EK_UNORM16) return __float_as_uint(__fadd_rz(t, MAGIC)) & 0xFFFFu;
+			else return (uint32_t)__float2int_rz(t) & 0xFFFFu;
+		}
+	}
+
+	// encode N consecutive elements into packed words (N * BYTES is a multiple of 4)
+	template <int N> static __device__ __forceinline__ void enc_pack(const uint32_t (&v)[N], uint32_t* out, uint32_t no_double) {
+		if constexpr (BYTES == 4) {
+#pragma unroll
+			for (int i = 0; i < N; ++i) out[i] = enc(v[i], no_double);
+		} else if constexpr (BYTES == 2) {
+#pragma unroll
+			for (int i = 0; i < N; i += 2) {
+				if constexpr (EK == FLMIP_EK_F16) {
+					// one F2FP.PACK_AB converts both halves
+					const __half2 h = __floats2half2_rn(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+					out[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+				} else {
+					out[i >> 1] = __byte_perm(enc(v[i], no_double), enc(v[i + 1], no_double), 0x5410u);
+				}
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < N; i += 4) {
+				const uint32_t lo = __byte_perm(enc(v[i], no_double), enc(v[i + 1], no_double), 0x0040u);
+				const uint32_t hi = __byte_perm(enc(v[i + 2], no_double), enc(v[i + 3], no_double), 0x0040u);
+				out[i >> 2] = __byte_perm(lo, hi, 0x5410u);
+			}
 		}
 	}
 
@@ -107,16 +173,6 @@ template <uint32_t EK> struct Codec {
 	}
 };
 
-template <int BYTES> __device__ __forceinline__ uint32_t get_elem(const uint32_t* w, int i) {
-	if constexpr (BYTES == 4) return w[i];
-	else if constexpr (BYTES == 2) return (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-	else return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-}
-template <int BYTES> __device__ __forceinline__ void put_elem(uint32_t* w, int i, uint32_t raw) {
-	if constexpr (BYTES == 4) w[i] = raw;
-	else if constexpr (BYTES == 2) w[i >> 1] |= raw << (16 * (i & 1));
-	else w[i >> 2] |= raw << (8 * (i & 3));
-}
 
 // texel load / store by size
 template <int BPP> struct TexelIO {
@@ -142,6 +198,7 @@ template <int BPP> struct TexelIO {
 	}
 };
 
+
 // ------------------------------------------------------------------------------------------------------
 // packed-row reductions: rows of NW 32-bit words holding whole texels -> NW/2 words of the next level
 // ------------------------------------------------------------------------------------------------------
@@ -149,19 +206,17 @@ template <uint32_t EK, int CH, int NW>
 __device__ __forceinline__ void reduce_rows_2d(const uint32_t (&r0)[NW], const uint32_t (&r1)[NW], uint32_t (&out)[NW / 2],
 											   uint32_t no_double) {
 	using C = Codec<EK>;
-	constexpr int NT = NW * 4 / (C::BYTES * CH); // texels per source row
-	static_assert(NT >= 2 && (NT % 2) == 0, "row must hold at least one x pair");
+	constexpr int NO = NW * 2 / C::BYTES; // output elements (= half the elements of one source row)
+	static_assert(NO >= CH && (NO % CH) == 0, "row must hold at least one x pair");
+	uint32_t v[NO];
 #pragma unroll
-	for (int i = 0; i < NW / 2; ++i) out[i] = 0;
-#pragma unroll
-	for (int p = 0; p < NT / 2; ++p) {
-#pragma unroll
-		for (int c = 0; c < CH; ++c) {
-			const uint32_t x0 = C::lerp_half(C::dec(get_elem<C::BYTES>(r0, (2 * p) * CH + c)), C::dec(get_elem<C::BYTES>(r0, (2 * p + 1) * CH + c)));
-			const uint32_t x1 = C::lerp_half(C::dec(get_elem<C::BYTES>(r1, (2 * p) * CH + c)), C::dec(get_elem<C::BYTES>(r1, (2 * p + 1) * CH + c)));
-			put_elem<C::BYTES>(out, p * CH + c, C::enc(C::lerp_half(x0, x1), no_double));
-		}
+	for (int e = 0; e < NO; ++e) {
+		const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
+		const uint32_t x0 = C::lerp_half(C::dec_at(r0, ea), C::dec_at(r0, eb));
+		const uint32_t x1 = C::lerp_half(C::dec_at(r1, ea), C::dec_at(r1, eb));
+		v[e] = C::lerp_half(x0, x1);
 	}
+	C::template enc_pack<NO>(v, out, no_double);
 }
 
 // r[z][y]: rows (y, y+1) of slices (z, z+1)
@@ -169,23 +224,19 @@ template <uint32_t EK, int CH, int NW>
 __device__ __forceinline__ void reduce_rows_3d(const uint32_t (&r00)[NW], const uint32_t (&r01)[NW], const uint32_t (&r10)[NW],
 											   const uint32_t (&r11)[NW], uint32_t (&out)[NW / 2], uint32_t no_double) {
 	using C = Codec<EK>;
-	constexpr int NT = NW * 4 / (C::BYTES * CH);
-	static_assert(NT >= 2 && (NT % 2) == 0, "row must hold at least one x pair");
+	constexpr int NO = NW * 2 / C::BYTES;
+	static_assert(NO >= CH && (NO % CH) == 0, "row must hold at least one x pair");
+	uint32_t v[NO];
 #pragma unroll
-	for (int i = 0; i < NW / 2; ++i) out[i] = 0;
-#pragma unroll
-	for (int p = 0; p < NT / 2; ++p) {
-#pragma unroll
-		for (int c = 0; c < CH; ++c) {
-			const int ea = (2 * p) * CH + c, eb = (2 * p + 1) * CH + c;
-			const uint32_t x00 = C::lerp_half(C::dec(get_elem<C::BYTES>(r00, ea)), C::dec(get_elem<C::BYTES>(r00, eb)));
-			const uint32_t x01 = C::lerp_half(C::dec(get_elem<C::BYTES>(r01, ea)), C::dec(get_elem<C::BYTES>(r01, eb)));
-			const uint32_t x10 = C::lerp_half(C::dec(get_elem<C::BYTES>(r10, ea)), C::dec(get_elem<C::BYTES>(r10, eb)));
-			const uint32_t x11 = C::lerp_half(C::dec(get_elem<C::BYTES>(r11, ea)), C::dec(get_elem<C::BYTES>(r11, eb)));
-			const uint32_t y0 = C::lerp_half(x00, x01), y1 = C::lerp_half(x10, x11);
-			put_elem<C::BYTES>(out, p * CH + c, C::enc(C::lerp_half(y0, y1), no_double));
-		}
+	for (int e = 0; e < NO; ++e) {
+		const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
+		const uint32_t x00 = C::lerp_half(C::dec_at(r00, ea), C::dec_at(r00, eb));
+		const uint32_t x01 = C::lerp_half(C::dec_at(r01, ea), C::dec_at(r01, eb));
+		const uint32_t x10 = C::lerp_half(C::dec_at(r10, ea), C::dec_at(r10, eb));
+		const uint32_t x11 = C::lerp_half(C::dec_at(r11, ea), C::dec_at(r11, eb));
+		v[e] = C::lerp_half(C::lerp_half(x00, x01), C::lerp_half(x10, x11));
 	}
+	C::template enc_pack<NO>(v, out, no_double);
 }
 
 // one destination texel from 4 / 8 individually addressed source texels (cascade levels)
@@ -206,7 +257,7 @@ __device__ __forceinline__ void reduce_texel(const uint8_t* src, uint32_t row_pi
 	for (int c = 0; c < CH; ++c) {
 		uint32_t v[DIMS == 3 ? 8 : 4];
 #pragma unroll
-		for (int k = 0; k < (DIMS == 3 ? 8 : 4); ++k) v[k] = C::dec(get_elem<C::BYTES>(t[k], c));
+		for (int k = 0; k < (DIMS == 3 ? 8 : 4); ++k) v[k] = C::dec_at(t[k], c);
 		uint32_t r = C::lerp_half(C::lerp_half(v[0], v[1]), C::lerp_half(v[2], v[3]));
 		if constexpr (DIMS == 3) r = C::lerp_half(r, C::lerp_half(C::lerp_half(v[4], v[5]), C::lerp_half(v[6], v[7])));
 		put_elem<C::BYTES>(out, c, C::enc(r, no_double));
@@ -252,6 +303,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 				 : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // ------------------------------------------------------------------------------------------------------
 // warp-level cascade over a dense region held in shared memory
 // ------------------------------------------------------------------------------------------------------
@@ -277,6 +331,7 @@ template <int DIMS> __device__ __forceinline__ bool next_level_has_texels(const 
 }
 
 // Executed by one full warp.  Reduces the region as far as it goes, writing every level to global memory.
+// All region sizes are powers of two, so texel indices decompose with shifts.
 template <uint32_t EK, int CH, int DIMS>
 __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Region& R, const flmip_fast_params& P, uint32_t layer,
 											 uint32_t lane) {
@@ -284,18 +339,19 @@ __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Regio
 	using IO = TexelIO<BPP>;
 	while (R.lvl + 1 < P.level_count && R.w >= 2 && R.h >= 2 && (DIMS < 3 || R.d >= 2)) {
 		const uint32_t dw = R.w >> 1, dh = R.h >> 1, dd = (DIMS == 3 ? R.d >> 1 : 1u);
+		const uint32_t sw = 31u - __clz(dw), sh = 31u - __clz(dh);
 		const uint32_t L = R.lvl + 1;
 		const uint32_t LW = P.dim[0] >> L, LH = P.dim[1] >> L;
 		uint8_t* gdst = level_layer_ptr<BPP, DIMS>(P, L, layer);
 		const uint32_t ox = R.ox >> 1, oy = R.oy >> 1, oz = R.oz >> 1;
 		const uint32_t row_pitch = R.w * BPP, slice_pitch = R.w * R.h * BPP;
 		for (uint32_t i = lane; i < dw * dh * dd; i += 32) {
-			const uint32_t x = i % dw, y = (i / dw) % dh, z = i / (dw * dh);
+			const uint32_t x = i & (dw - 1u), y = (i >> sw) & (dh - 1u), z = i >> (sw + sh);
 			uint32_t out[IO::NW];
 			reduce_texel<EK, CH, DIMS, false>(src + (size_t)(2 * z) * slice_pitch + (size_t)(2 * y) * row_pitch + (size_t)(2 * x) * BPP,
 											  row_pitch, slice_pitch, out, P.no_double);
 			IO::store(dst + (size_t)i * BPP, out);
-			IO::store(gdst + ((uint64_t)(oz + z) * LH * LW + (uint64_t)(oy + y) * LW + (ox + x)) * BPP, out);
+			if (!(P.debug_flags & 2u)) IO::store(gdst + ((uint64_t)(oz + z) * LH * LW + (uint64_t)(oy + y) * LW + (ox + x)) * BPP, out);
 		}
 		__syncwarp();
 		uint8_t* t = src; src = dst; dst = t;
@@ -303,222 +359,543 @@ __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Regio
 	}
 }
 
-// copies a region of global level `R.lvl` (written by other CTAs) into shared memory, bypassing L1
+// copies a region of global level `R.lvl` (written by other CTAs) into shared memory, bypassing L1.
+// Loads are issued in batches per lane: under load a round trip to L2 costs microseconds.
 template <int BPP, int DIMS>
 __device__ __forceinline__ void gather_region(uint8_t* smem_dst, const Region& R, const flmip_fast_params& P, uint32_t layer, uint32_t lane) {
 	using IO = TexelIO<BPP>;
+	constexpr uint32_t U = (IO::NW >= 4 ? 2u : (IO::NW == 2 ? 4u : 8u)); // <= 8 registers of payload in flight
 	const uint32_t LW = P.dim[0] >> R.lvl, LH = P.dim[1] >> R.lvl;
+	const uint32_t sw = 31u - __clz(R.w), sh = 31u - __clz(R.h);
 	const uint8_t* g = level_layer_ptr<BPP, DIMS>(P, R.lvl, layer);
-	for (uint32_t i = lane; i < R.w * R.h * R.d; i += 32) {
-		const uint32_t x = i % R.w, y = (i / R.w) % R.h, z = i / (R.w * R.h);
-		uint32_t t[IO::NW];
-		IO::template load<true>(g + ((uint64_t)(R.oz + z) * LH * LW + (uint64_t)(R.oy + y) * LW + (R.ox + x)) * BPP, t);
-		IO::store(smem_dst + (size_t)i * BPP, t);
+	const uint32_t n = R.w * R.h * R.d;
+	for (uint32_t base = 0; base < n; base += 32u * U) {
+		uint32_t t[U][IO::NW];
+#pragma unroll
+		for (uint32_t u = 0; u < U; ++u) {
+			const uint32_t i = base + u * 32u + lane;
+			if (i < n) {
+				const uint32_t x = i & (R.w - 1u), y = (i >> sw) & (R.h - 1u), z = i >> (sw + sh);
+				IO::template load<true>(g + ((uint64_t)(R.oz + z) * LH * LW + (uint64_t)(R.oy + y) * LW + (R.ox + x)) * BPP, t[u]);
+			}
+		}
+#pragma unroll
+		for (uint32_t u = 0; u < U; ++u) {
+			const uint32_t i = base + u * 32u + lane;
+			if (i < n) IO::store(smem_dst + (size_t)i * BPP, t[u]);
+		}
 	}
 	__syncwarp();
 }
 
 // classic "last block" protocol (threadfence + atomic ticket); returns true for the warp that arrives last.
 // The counter is reset by that warp, so a relaunch needs no memset.
+// Release / acquire ride on the atomic itself (atom.acq_rel.gpu) instead of a sequentially consistent __threadfence():
+// the other lanes' stores are ordered before it by __syncwarp (cumulativity), their later loads after it likewise.
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+	uint32_t old;
+	asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+	return old;
+}
 __device__ __forceinline__ bool arrive_last(uint32_t* counter, uint32_t expected, uint32_t lane) {
-	__threadfence();
 	__syncwarp();
 	uint32_t last = 0;
 	if (lane == 0) {
-		const uint32_t old = atomicAdd(counter, 1u);
+		const uint32_t old = atom_add_acq_rel_gpu(counter, 1u);
 		last = (old == expected - 1u);
 		if (last) *counter = 0u;
 	}
 	last = __shfl_sync(0xFFFFFFFFu, last, 0);
-	if (last) __threadfence();
 	return last != 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
-// the single-pass kernel
+// the single-pass kernel: persistent CTAs, TMA producer warp + 8 consumer warps, `stages`-deep tile ring
 // ------------------------------------------------------------------------------------------------------
+// A "unit" is what one CTA works through in one go and what gets published to the other CTAs: 2 x 2 (x 2) adjacent
+// tiles (unit_shift = 1) or a single tile (unit_shift = 0, images fewer than two tiles wide).  Tile index = unit * tiles
+// per unit + sub-tile.
+struct TileCoord {
+	uint32_t x, y, z, layer; // tile coordinates
+	uint32_t ux, uy, uz, k;  // unit coordinates, sub-tile within the unit
+};
+template <int DIMS> __device__ __forceinline__ TileCoord tile_coord(const flmip_fast_params& P, uint32_t t) {
+	TileCoord c;
+	const uint32_t us = P.unit_shift;
+	c.k = t & ((1u << (us * DIMS)) - 1u);
+	uint32_t u = t >> (us * DIMS);
+	c.ux = u & (P.units[0] - 1u); u >>= P.unit_cshift[0];
+	c.uy = u & (P.units[1] - 1u); u >>= P.unit_cshift[1];
+	if constexpr (DIMS == 3) { c.uz = u & (P.units[2] - 1u); c.layer = u >> P.unit_cshift[2]; }
+	else { c.uz = 0; c.layer = u; }
+	c.x = (c.ux << us) | (c.k & us);
+	c.y = (c.uy << us) | ((c.k >> 1) & us);
+	c.z = (c.uz << us) | ((c.k >> 2) & us);
+	return c;
+}
+
+// Levels IN_REG_LEVELS+1 .. of one tile from the tile's cascade slot; returns the tile's remainder region.
+// Runs on a finisher warp, off the consumers' critical path.
+template <uint32_t EK, int CH, int DIMS>
+__device__ __forceinline__ Region finish_tile(uint8_t* buf_a, uint8_t* buf_b, const flmip_fast_params& P, const TileCoord& tc, uint32_t lane,
+											  uint8_t*& remainder) {
+	using C = Codec<EK>;
+	constexpr int BPP = C::BYTES * CH;
+	using TL = flmip_tiling<BPP, DIMS>;
+	constexpr uint32_t S0 = TL::IN_REG_LEVELS; // level held in buf_a
+	Region R;
+	R.lvl = S0;
+	R.w = TL::TX >> S0; R.h = TL::TY >> S0; R.d = (DIMS == 3 ? TL::TZ >> S0 : 1u);
+	R.ox = tc.x * R.w; R.oy = tc.y * R.h; R.oz = (DIMS == 3 ? tc.z * R.d : 0u);
+	uint8_t *src = buf_a, *dst = buf_b;
+	cascade_warp<EK, CH, DIMS>(src, dst, R, P, tc.layer, lane);
+	remainder = src; // the texels of level R.lvl this tile ends on
+	return R;
+}
+
+// debug trace: (type, cta, ns) records appended to the instrumentation area when debug flag 512 is set
+__device__ __forceinline__ void dbg_trace(const flmip_fast_params& P, uint32_t type, uint32_t extra = 0) {
+	if (!(P.debug_flags & 512u)) return;
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	unsigned long long* d = reinterpret_cast<unsigned long long*>(P.counters) + P.debug_off;
+	const unsigned long long idx = atomicAdd(d + 16, 1ull);
+	if (idx < 200000ull) {
+		d[32 + 2 * idx] = ((unsigned long long)type << 48) | ((unsigned long long)extra << 24) | blockIdx.x;
+		d[33 + 2 * idx] = t;
+	}
+}
+
+// Group bookkeeping of a unit: its group's counters and how many units the group has.
+template <int BPP, int DIMS> struct GroupOf {
+	using TL = flmip_tiling<BPP, DIMS>;
+	static constexpr uint32_t G = TL::GROUP;
+	static constexpr uint32_t GS = (uint32_t)flmip_ilog2(G);
+	uint32_t gx, gy, gz, ntx, nty, ntz;
+	__device__ __forceinline__ GroupOf(const flmip_fast_params& P, const TileCoord& tc) { // G x G (x G) units
+		gx = tc.ux >> GS; gy = tc.uy >> GS; gz = (DIMS == 3 ? tc.uz >> GS : 0u);
+		ntx = min(G, P.units[0] - gx * G); nty = min(G, P.units[1] - gy * G); ntz = (DIMS == 3 ? min(G, P.units[2] - gz * G) : 1u);
+	}
+	__device__ __forceinline__ uint64_t index(const flmip_fast_params& P, uint32_t layer) const {
+		const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
+		return (uint64_t)layer * groups_per_layer + (gz * P.groups[1] + gy) * P.groups[0] + gx;
+	}
+	// Two-step arrival.  Tiles that are in flight at the same time are neighbours along x, and the L2 atomic unit
+	// serialises operations on one address: a tile first arrives on the counter of its COLUMN within the group
+	// (G counters per group, FLMIP_COLUMN_COUNTER_STRIDE words apart), the last tile of a column on the group counter.
+	__device__ __forceinline__ uint32_t* column_counter(const flmip_fast_params& P, uint32_t layer, uint32_t unit_x) const {
+		return reinterpret_cast<uint32_t*>(P.column_counters) + (index(P, layer) * G + (unit_x & (G - 1u))) * FLMIP_COLUMN_COUNTER_STRIDE;
+	}
+	__device__ __forceinline__ uint32_t column_tiles() const { return nty * ntz; }
+	__device__ __forceinline__ uint32_t* counter(const flmip_fast_params& P, uint32_t layer) const {
+		return reinterpret_cast<uint32_t*>(P.counters) + index(P, layer);
+	}
+	__device__ __forceinline__ uint32_t columns() const { return ntx; }
+};
+
+// Last arriver of a group of units: reduces the group's patch and, if its group is the last one of the layer, the rest of
+// the chain.  Runs in the CTA's patch buffer, serialised between the finisher warps of a CTA by a shared-memory lock.
+template <uint32_t EK, int CH, int DIMS>
+__device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b, uint32_t* patch_lock, const flmip_fast_params& P,
+											 const TileCoord& tc, Region R, uint32_t lane) {
+	using C = Codec<EK>;
+	constexpr int BPP = C::BYTES * CH;
+	using TL = flmip_tiling<BPP, DIMS>;
+	constexpr uint32_t G = TL::GROUP;
+	const uint32_t layer = tc.layer;
+	const GroupOf<BPP, DIMS> grp(P, tc);
+
+	if (lane == 0) dbg_trace(P, 3);
+	unsigned long long dbg_t0 = 0, dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0;
+	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+	if (lane == 0) {
+		while (atomicCAS(patch_lock, 0u, 1u) != 0u) __nanosleep(64);
+	}
+	__syncwarp();
+	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+	if (lane == 0) dbg_trace(P, 7);
+	// patch = this group's part of the level the units ended on (R.w/h/d are the per-unit remainders here)
+	R.ox = grp.gx * G * R.w; R.oy = grp.gy * G * R.h; R.oz = grp.gz * G * R.d;
+	R.w *= grp.ntx; R.h *= grp.nty; R.d *= grp.ntz;
+	uint8_t *src = patch_a, *dst = patch_b;
+	if (!(P.debug_flags & 128u)) gather_region<BPP, DIMS>(src, R, P, layer, lane);
+	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t2));
+	if (lane == 0) dbg_trace(P, 8);
+	if (!(P.debug_flags & 256u)) cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t3));
+	if (lane == 0) dbg_trace(P, 9);
+
+	// ---- layer stage: the last group of a layer finishes the chain -----------------------------------------
+	const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
+	if (next_level_has_texels<DIMS>(P, R.lvl) &&
+		arrive_last(reinterpret_cast<uint32_t*>(P.counters) + (uint64_t)P.layers * groups_per_layer + layer, groups_per_layer, lane)) {
+		if (lane == 0) dbg_trace(P, 10);
+		R.ox = R.oy = R.oz = 0;
+		R.w = P.dim[0] >> R.lvl; R.h = P.dim[1] >> R.lvl; R.d = (DIMS == 3 ? P.dim[2] >> R.lvl : 1u);
+		src = patch_a; dst = patch_b;
+		gather_region<BPP, DIMS>(src, R, P, layer, lane);
+		if (lane == 0) dbg_trace(P, 11);
+		cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		__threadfence_block();
+		atomicExch(patch_lock, 0u);
+	}
+	if (lane == 0) dbg_trace(P, 4);
+	if ((P.debug_flags & 64u) && lane == 0) {
+		unsigned long long dbg_t4;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t4));
+		unsigned long long* d = reinterpret_cast<unsigned long long*>(P.counters) + P.debug_off;
+		atomicAdd(d + 0, 1ull);
+		atomicAdd(d + 1, dbg_t1 - dbg_t0); // lock
+		atomicAdd(d + 2, dbg_t2 - dbg_t1); // gather
+		atomicAdd(d + 3, dbg_t3 - dbg_t2); // cascade
+		atomicAdd(d + 4, dbg_t4 - dbg_t3); // layer stage + unlock
+		atomicMax(d + 5, dbg_t4 - dbg_t0);
+	}
+}
+
+// warp roles of one persistent CTA
+constexpr int FLMIP_CONSUMER_WARPS = 8;                           // warps 0..7: tile -> levels 1 (+2) in registers
+constexpr int FLMIP_CONSUMER_THREADS = FLMIP_CONSUMER_WARPS * 32;
+constexpr int FLMIP_PRODUCER_WARP = FLMIP_CONSUMER_WARPS;         // warp 8: TMA loads
+constexpr int FLMIP_FINISHER_WARP0 = FLMIP_PRODUCER_WARP + 1;     // warps 9..: remaining levels of a tile + last-arriver stages
+static_assert(FLMIP_BLOCK_THREADS == (FLMIP_FINISHER_WARP0 + FLMIP_FINISHER_WARPS) * 32, "block size out of sync with mip_params.h");
+
 template <uint32_t EK, int CH, int DIMS>
 __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_fast_params& P) {
 	using C = Codec<EK>;
 	constexpr int BPP = C::BYTES * CH;
 	using TL = flmip_tiling<BPP, DIMS>;
-	constexpr int TPC = 16 / BPP;                 // texels per 16-byte chunk (0 if BPP == 16 -> handled as 1 chunk = 1 texel)
 	constexpr bool WIDE = (BPP == 16);            // x pair spans the two chunks of a thread
 	constexpr int ROW_BYTES = TL::TILE_BYTES_X;   // bytes of one tile row in shared memory
-	(void)TPC;
+	static_assert(TL::THREADS == FLMIP_CONSUMER_THREADS, "one consumer thread per 32 B x 4 rows (2D) / 32 B x 2 x 2 (3D)");
 
-	extern __shared__ __align__(128) uint8_t smem_raw[]; // TMA destination: 128-byte aligned
-	uint8_t* tile = smem_raw;
-	uint8_t* buf_a = tile + TL::TILE_BYTES;
-	uint8_t* buf_b = buf_a + TL::CASCADE_BYTES;
-	__shared__ uint64_t mbar;
+	// [stages x tile][FLMIP_FINISHER_WARPS cascade slots (buf_a, buf_b)][patch buffer]; tiles are TMA destinations: 128-byte aligned
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	__shared__ uint64_t full_bar[FLMIP_MAX_STAGES], empty_bar[FLMIP_MAX_STAGES];
+	__shared__ uint64_t slot_full[FLMIP_FINISHER_WARPS], slot_empty[FLMIP_FINISHER_WARPS];
+	__shared__ uint32_t finisher_ticket, patch_lock, unit_count[2];
+	__shared__ __align__(16) uint8_t unit_patch[2][FLMIP_UNIT_PATCH_BYTES + FLMIP_UNIT_PATCH_BYTES / 4u];
+	__shared__ uint32_t stage_tile[FLMIP_MAX_STAGES], slot_tile[FLMIP_FINISHER_WARPS]; // tile index riding along with the data
+	const uint32_t stages = P.stages;
+	uint8_t* const cascade_base = smem_raw + (size_t)stages * TL::TILE_BYTES;
 
-	const uint32_t tid = threadIdx.x, lane = tid & 31u;
-
-	// tile coordinates
-	uint32_t b = blockIdx.x;
-	const uint32_t tile_x = b % P.tiles[0]; b /= P.tiles[0];
-	const uint32_t tile_y = b % P.tiles[1]; b /= P.tiles[1];
-	uint32_t tile_z = 0, layer = 0;
-	if constexpr (DIMS == 3) { tile_z = b % P.tiles[2]; layer = b / P.tiles[2]; }
-	else { layer = b; }
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
 	if (tid == 0) {
-		mbar_init(&mbar, 1);
+		finisher_ticket = 0;
+		patch_lock = 0;
+		unit_count[0] = unit_count[1] = 0;
+		for (uint32_t s = 0; s < stages; ++s) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], FLMIP_CONSUMER_WARPS);
+		}
+		for (uint32_t f = 0; f < FLMIP_FINISHER_WARPS; ++f) {
+			mbar_init(&slot_full[f], FLMIP_CONSUMER_WARPS);
+			mbar_init(&slot_empty[f], 1);
+		}
 		fence_mbar_init();
 	}
 	__syncthreads();
-	if (tid == 0) {
-		mbar_arrive_expect_tx(&mbar, TL::TILE_BYTES);
-		// innermost coordinate in uint32 units; 2D images use the third tensor dim for the layer
-		tma_load_3d(tile, &tmap, &mbar, (int)(tile_x * (ROW_BYTES / 4)), (int)(tile_y * TL::TY), (int)(DIMS == 3 ? tile_z * TL::TZ : layer));
-	}
-	mbar_wait(&mbar, 0);
 
-	uint8_t* const g1 = level_layer_ptr<BPP, DIMS>(P, 1, layer);
-	const uint64_t l1_pitch = (uint64_t)(P.dim[0] >> 1) * BPP; // bytes per level-1 row
-
-	if constexpr (DIMS == 2) {
-		// thread = 2 chunks (32 B) x 4 rows; quarter-warps read conflict-free by swapping the chunk order on lane bit 2
-		const uint32_t tx = tid % TL::THREADS_X, ty = tid / TL::THREADS_X;
-		const uint32_t sel = (lane >> 2) & 1u;
-		uint32_t raw[4][2][4];
-#pragma unroll
-		for (int r = 0; r < 4; ++r) {
-#pragma unroll
-			for (int k = 0; k < 2; ++k) {
-				const uint4 v = *reinterpret_cast<const uint4*>(tile + (4 * ty + r) * ROW_BYTES + (2 * tx + (k ^ sel)) * 16);
-				raw[r][k][0] = v.x; raw[r][k][1] = v.y; raw[r][k][2] = v.z; raw[r][k][3] = v.w;
-			}
-		}
-		uint32_t l1[2][4]; // two level-1 rows of 16 bytes, logical (left, right) order
-		if constexpr (!WIDE) {
-#pragma unroll
-			for (int j = 0; j < 2; ++j) {
-				uint32_t o0[2], o1[2];
-				reduce_rows_2d<EK, CH, 4>(raw[2 * j][0], raw[2 * j + 1][0], o0, P.no_double);
-				reduce_rows_2d<EK, CH, 4>(raw[2 * j][1], raw[2 * j + 1][1], o1, P.no_double);
-				l1[j][0] = sel ? o1[0] : o0[0]; l1[j][1] = sel ? o1[1] : o0[1];
-				l1[j][2] = sel ? o0[0] : o1[0]; l1[j][3] = sel ? o0[1] : o1[1];
-			}
-		} else {
-#pragma unroll
-			for (int j = 0; j < 2; ++j) {
-				uint32_t ra[8], rb[8];
-#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					ra[i] = sel ? raw[2 * j][1][i] : raw[2 * j][0][i];
-					ra[4 + i] = sel ? raw[2 * j][0][i] : raw[2 * j][1][i];
-					rb[i] = sel ? raw[2 * j + 1][1][i] : raw[2 * j + 1][0][i];
-					rb[4 + i] = sel ? raw[2 * j + 1][0][i] : raw[2 * j + 1][1][i];
+	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
+	// the finisher pool is idle when the consumers' in-register levels end the chain
+	const bool need_finish = P.level_count > TL::IN_REG_LEVELS + 1u && !(P.debug_flags & 1u);
+	if (warp >= FLMIP_FINISHER_WARP0) {
+		// ---- finishers: a pool of warps that take the CTA's tiles in ring order by ticket ---------------------
+		if (!need_finish) return; // the consumers produce every level
+		uint8_t* const patch_a = cascade_base + FLMIP_FINISHER_WARPS * SLOT_BYTES;
+		uint8_t* const patch_b = patch_a + TL::CASCADE_BYTES;
+		const uint32_t kbits = P.unit_shift * DIMS;      // log2(tiles per unit)
+		const uint32_t unit_tiles = 1u << kbits;
+		for (;;) {
+			uint32_t n = 0;
+			if (lane == 0) n = atomicAdd(&finisher_ticket, 1u);
+			n = __shfl_sync(0xFFFFFFFFu, n, 0);
+			const uint32_t slot = n % FLMIP_FINISHER_WARPS, use = n / FLMIP_FINISHER_WARPS;
+			uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
+			mbar_wait(&slot_full[slot], use & 1u);
+			const uint32_t t = slot_tile[slot];
+			if (t == FLMIP_NO_TILE) break; // the consumers are done: one sentinel per finisher warp
+			const TileCoord tc = tile_coord<DIMS>(P, t);
+			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 12, n);
+			uint8_t* rem = nullptr;
+			Region R = finish_tile<EK, CH, DIMS>(buf_a, buf_a + TL::CASCADE_BYTES, P, tc, lane, rem);
+			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 13, n);
+			bool carry_on = next_level_has_texels<DIMS>(P, R.lvl);
+			if (carry_on && kbits != 0) {
+				// ---- unit stage: the remainders of the unit's tiles meet in shared memory; whoever brings the last one
+				//      reduces them one more level.  The CTA works through its units in order, two buffers suffice
+				//      (a slot is only released after its tile is in, and FLMIP_FINISHER_WARPS <= tiles per unit + 1).
+				const uint32_t q = (n >> kbits) & 1u;
+				uint8_t* const up = unit_patch[q];
+				const uint32_t kx = tc.k & 1u, ky = (tc.k >> 1) & 1u, kz = (DIMS == 3 ? tc.k >> 2 : 0u);
+				const uint32_t sw = 31u - __clz(R.w), sh = 31u - __clz(R.h);
+				for (uint32_t i = lane; i < R.w * R.h * R.d; i += 32) {
+					const uint32_t x = i & (R.w - 1u), y = (i >> sw) & (R.h - 1u), z = i >> (sw + sh);
+					uint32_t texel[TexelIO<BPP>::NW];
+					TexelIO<BPP>::template load<false>(rem + (size_t)i * BPP, texel);
+					TexelIO<BPP>::store(up + ((size_t)((kz * R.d + z) * (2u * R.h) + ky * R.h + y) * (2u * R.w) + kx * R.w + x) * BPP, texel);
 				}
-				reduce_rows_2d<EK, CH, 8>(ra, rb, l1[j], P.no_double);
+				__syncwarp();
+				uint32_t last = 0;
+				if (lane == 0) {
+					__threadfence_block();
+					last = (atomicAdd(&unit_count[q], 1u) == unit_tiles - 1u);
+					if (last) {
+						unit_count[q] = 0u;
+						__threadfence_block();
+					}
+				}
+				carry_on = __shfl_sync(0xFFFFFFFFu, last, 0) != 0;
+				if (carry_on) {
+					R.w *= 2u; R.h *= 2u; if (DIMS == 3) R.d *= 2u;
+					R.ox = tc.ux * R.w; R.oy = tc.uy * R.h; R.oz = (DIMS == 3 ? tc.uz * R.d : 0u);
+					uint8_t *src = up, *dst = up + FLMIP_UNIT_PATCH_BYTES;
+					cascade_warp<EK, CH, DIMS>(src, dst, R, P, tc.layer, lane);
+					carry_on = next_level_has_texels<DIMS>(P, R.lvl);
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_empty[slot]); // the slot is free again before the slow part starts
+			if (!carry_on) continue;
+			// publish the unit; the last arriver of its group carries on
+			const GroupOf<BPP, DIMS> grp(P, tc);
+			const bool last = arrive_last(grp.column_counter(P, tc.layer, tc.ux), grp.column_tiles(), lane) && arrive_last(grp.counter(P, tc.layer), grp.columns(), lane);
+			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 14, n);
+			if (last) finish_group<EK, CH, DIMS>(patch_a, patch_b, &patch_lock, P, tc, R, lane);
+		}
+		return;
+	}
+	if (warp == FLMIP_PRODUCER_WARP) {
+		// ---- producer: dynamic tile scheduler + TMA issue ----------------------------------------------------
+		// Units are handed out by a global atomic counter, so an SM that gets less memory bandwidth simply takes
+		// fewer of them.  An atomic round trip costs microseconds under load: lanes 0..PF-1 each keep one fetch in
+		// flight, lane (it % PF) holds the tile of iteration `it`.
+		constexpr uint32_t PF = FLMIP_SCHED_PREFETCH;
+		uint32_t* const sched = reinterpret_cast<uint32_t*>(P.sched);
+		uint32_t pf = FLMIP_NO_TILE;
+		if (lane < PF) pf = atomicAdd(&sched[0], 1u);
+		uint32_t s = 0, use = 0, dead = 0;
+		const uint32_t kbits = P.unit_shift * DIMS;
+		for (uint32_t it = 0; dead < PF; ++it) {
+			const uint32_t u = __shfl_sync(0xFFFFFFFFu, pf, it % PF);
+			if (u >= P.total_units) { ++dead; continue; } // this lane ran off the end; the others may still hold units
+			dead = 0;
+			if (lane == it % PF) pf = atomicAdd(&sched[0], 1u); // unit of iteration it + PF
+			if (lane == 0) {
+				for (uint32_t k = 0; k < (1u << kbits); ++k) {
+					const uint32_t t = (u << kbits) | k;
+					if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
+					const TileCoord tc = tile_coord<DIMS>(P, t);
+					stage_tile[s] = t;
+					mbar_arrive_expect_tx(&full_bar[s], TL::TILE_BYTES);
+					// innermost coordinate in uint32 units; 2D images use the third tensor dim for the layer
+					tma_load_3d(smem_raw + (size_t)s * TL::TILE_BYTES, &tmap, &full_bar[s], (int)(tc.x * (ROW_BYTES / 4)), (int)(tc.y * TL::TY),
+								(int)(DIMS == 3 ? tc.z * TL::TZ : tc.layer));
+					if (++s == stages) { s = 0; ++use; }
+				}
+			}
+			// every lane tracks the ring position
+			if (lane != 0) {
+				const uint32_t adv = s + (1u << kbits);
+				use += adv / stages;
+				s = adv % stages;
+			}
+			__syncwarp();
+		}
+		if (lane == 0) {
+			// end of work: a sentinel instead of a tile
+			if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
+			stage_tile[s] = FLMIP_NO_TILE;
+			mbar_arrive(&full_bar[s]);
+			// the last producer to get here re-arms the scheduler for the next launch (every fetch has been made by then)
+			__threadfence();
+			if (atomicAdd(&sched[1], 1u) == gridDim.x - 1u) {
+				sched[0] = 0u;
+				sched[1] = 0u;
 			}
 		}
-		// level 1: one 16-byte store per row
+		return;
+	}
+
+	// ---- consumers ------------------------------------------------------------------------------------------
+	// No barrier couples the consumer warps: each walks the tile ring on its own, so warps of one CTA overlap
+	// different tiles.
+	const uint32_t sel = (lane >> 2) & 1u; // quarter-warps read conflict-free by swapping the chunk order on lane bit 2
+	uint32_t s = 0, use = 0, slot = 0, slot_use = 0;
+	if (tid == 0) dbg_trace(P, 1);
+	for (uint32_t it = 0;; ++it) {
+		mbar_wait(&full_bar[s], use & 1u);
+		const uint32_t t = stage_tile[s];
+		if (t == FLMIP_NO_TILE) break;
+		if (tid == 0 && (it & 7u) == 0) dbg_trace(P, 5, it);
+		const TileCoord tc = tile_coord<DIMS>(P, t);
+		const uint32_t tile_x = tc.x, tile_y = tc.y, tile_z = tc.z, layer = tc.layer;
+		const uint8_t* const tile = smem_raw + (size_t)s * TL::TILE_BYTES;
+		uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
+		uint8_t* const g1 = level_layer_ptr<BPP, DIMS>(P, 1, layer);
+		const uint64_t l1_pitch = (uint64_t)(P.dim[0] >> 1) * BPP; // bytes per level-1 row
+
+		if constexpr (DIMS == 2) {
+			// thread = 2 chunks (32 B) x 4 rows
+			const uint32_t tx = tid % TL::THREADS_X, ty = tid / TL::THREADS_X;
+			uint32_t raw[4][2][4];
 #pragma unroll
-		for (int j = 0; j < 2; ++j) {
-			const uint32_t row = tile_y * (TL::TY / 2) + 2 * ty + j;
-			*reinterpret_cast<uint4*>(g1 + (uint64_t)row * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
-				make_uint4(l1[j][0], l1[j][1], l1[j][2], l1[j][3]);
-		}
-		if constexpr (!WIDE) {
-			// level 2 in registers: 8 bytes per thread
-			if (P.level_count > 2) {
-				uint32_t l2[2];
-				reduce_rows_2d<EK, CH, 4>(l1[0], l1[1], l2, P.no_double);
-				uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
-				const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
-				const uint32_t row = tile_y * (TL::TY / 4) + ty;
-				*reinterpret_cast<uint2*>(g2 + (uint64_t)row * l2_pitch + (uint64_t)tile_x * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
-				*reinterpret_cast<uint2*>(buf_a + ty * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
-			}
-		} else {
-#pragma unroll
-			for (int j = 0; j < 2; ++j) {
-				*reinterpret_cast<uint4*>(buf_a + (2 * ty + j) * (ROW_BYTES / 2) + tx * 16) = make_uint4(l1[j][0], l1[j][1], l1[j][2], l1[j][3]);
-			}
-		}
-	} else {
-		// 3D: thread = 2 chunks x 2 rows x 2 slices -> 16 bytes of level 1
-		const uint32_t tx = tid % TL::THREADS_X, ty = (tid / TL::THREADS_X) % TL::THREADS_Y, tz = tid / (TL::THREADS_X * TL::THREADS_Y);
-		const uint32_t sel = (lane >> 2) & 1u;
-		static_assert(TL::THREADS_X == 4, "bank-conflict swizzle assumes 4 chunk pairs per tile row");
-		uint32_t raw[2][2][2][4]; // [slice][row][k]
-#pragma unroll
-		for (int s = 0; s < 2; ++s) {
-#pragma unroll
-			for (int r = 0; r < 2; ++r) {
+			for (int r = 0; r < 4; ++r) {
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
-					const uint4 v = *reinterpret_cast<const uint4*>(tile + ((2 * tz + s) * TL::TY + (2 * ty + r)) * ROW_BYTES + (2 * tx + (k ^ sel)) * 16);
-					raw[s][r][k][0] = v.x; raw[s][r][k][1] = v.y; raw[s][r][k][2] = v.z; raw[s][r][k][3] = v.w;
+					const uint4 v = *reinterpret_cast<const uint4*>(tile + (4 * ty + r) * ROW_BYTES + (2 * tx + (k ^ sel)) * 16);
+					raw[r][k][0] = v.x; raw[r][k][1] = v.y; raw[r][k][2] = v.z; raw[r][k][3] = v.w;
 				}
 			}
-		}
-		uint32_t l1[4];
-		if constexpr (!WIDE) {
-			uint32_t o0[2], o1[2];
-			reduce_rows_3d<EK, CH, 4>(raw[0][0][0], raw[0][1][0], raw[1][0][0], raw[1][1][0], o0, P.no_double);
-			reduce_rows_3d<EK, CH, 4>(raw[0][0][1], raw[0][1][1], raw[1][0][1], raw[1][1][1], o1, P.no_double);
-			l1[0] = sel ? o1[0] : o0[0]; l1[1] = sel ? o1[1] : o0[1];
-			l1[2] = sel ? o0[0] : o1[0]; l1[3] = sel ? o0[1] : o1[1];
-		} else {
-			uint32_t rr[2][2][8];
+			// the tile now lives in registers: hand the stage back to the producer
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+			uint32_t l1[2][4]; // two level-1 rows of 16 bytes, logical (left, right) order
+			if constexpr (!WIDE) {
 #pragma unroll
-			for (int s = 0; s < 2; ++s)
+				for (int j = 0; j < 2; ++j) {
+					uint32_t o0[2], o1[2];
+					reduce_rows_2d<EK, CH, 4>(raw[2 * j][0], raw[2 * j + 1][0], o0, P.no_double);
+					reduce_rows_2d<EK, CH, 4>(raw[2 * j][1], raw[2 * j + 1][1], o1, P.no_double);
+					l1[j][0] = sel ? o1[0] : o0[0]; l1[j][1] = sel ? o1[1] : o0[1];
+					l1[j][2] = sel ? o0[0] : o1[0]; l1[j][3] = sel ? o0[1] : o1[1];
+				}
+			} else {
 #pragma unroll
-				for (int r = 0; r < 2; ++r)
+				for (int j = 0; j < 2; ++j) {
+					uint32_t ra[8], rb[8];
 #pragma unroll
 					for (int i = 0; i < 4; ++i) {
-						rr[s][r][i] = sel ? raw[s][r][1][i] : raw[s][r][0][i];
-						rr[s][r][4 + i] = sel ? raw[s][r][0][i] : raw[s][r][1][i];
+						ra[i] = sel ? raw[2 * j][1][i] : raw[2 * j][0][i];
+						ra[4 + i] = sel ? raw[2 * j][0][i] : raw[2 * j][1][i];
+						rb[i] = sel ? raw[2 * j + 1][1][i] : raw[2 * j + 1][0][i];
+						rb[4 + i] = sel ? raw[2 * j + 1][0][i] : raw[2 * j + 1][1][i];
 					}
-			reduce_rows_3d<EK, CH, 8>(rr[0][0], rr[0][1], rr[1][0], rr[1][1], l1, P.no_double);
+					reduce_rows_2d<EK, CH, 8>(ra, rb, l1[j], P.no_double);
+				}
+			}
+			// level 1: one 16-byte store per row
+#pragma unroll
+			for (int j = 0; j < 2; ++j) {
+				const uint32_t row = tile_y * (TL::TY / 2) + 2 * ty + j;
+				*reinterpret_cast<uint4*>(g1 + (uint64_t)row * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
+					make_uint4(l1[j][0], l1[j][1], l1[j][2], l1[j][3]);
+			}
+			if constexpr (!WIDE) {
+				// level 2 in registers: 8 bytes per thread
+				if (P.level_count > 2) {
+					uint32_t l2[2];
+					reduce_rows_2d<EK, CH, 4>(l1[0], l1[1], l2, P.no_double);
+					uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
+					const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
+					const uint32_t row = tile_y * (TL::TY / 4) + ty;
+					*reinterpret_cast<uint2*>(g2 + (uint64_t)row * l2_pitch + (uint64_t)tile_x * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
+					if (need_finish) {
+						if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+						*reinterpret_cast<uint2*>(buf_a + ty * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
+					}
+				}
+			} else {
+				// 16-byte texels: a thread holds one level-1 texel per row, its x neighbour lives in lane ^ 1.
+				// Even lanes fetch it with shuffles and produce the level-2 texel.
+				if (P.level_count > 2) {
+					uint32_t ra[8], rb[8];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						ra[i] = l1[0][i]; rb[i] = l1[1][i];
+						ra[4 + i] = __shfl_xor_sync(0xFFFFFFFFu, l1[0][i], 1);
+						rb[4 + i] = __shfl_xor_sync(0xFFFFFFFFu, l1[1][i], 1);
+					}
+					if (!(lane & 1u)) {
+						uint32_t l2[4];
+						reduce_rows_2d<EK, CH, 8>(ra, rb, l2, P.no_double);
+						uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
+						const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
+						const uint32_t row = tile_y * (TL::TY / 4) + ty;
+						*reinterpret_cast<uint4*>(g2 + (uint64_t)row * l2_pitch + (uint64_t)tile_x * (ROW_BYTES / 4) + (tx >> 1) * 16) =
+							make_uint4(l2[0], l2[1], l2[2], l2[3]);
+						if (need_finish) {
+							if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+							*reinterpret_cast<uint4*>(buf_a + ty * (ROW_BYTES / 4) + (tx >> 1) * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+						}
+					}
+				}
+			}
+		} else {
+			// 3D: thread = 2 chunks x 2 rows x 2 slices -> 16 bytes of level 1
+			const uint32_t tx = tid % TL::THREADS_X, ty = (tid / TL::THREADS_X) % TL::THREADS_Y, tz = tid / (TL::THREADS_X * TL::THREADS_Y);
+			static_assert(TL::THREADS_X == 4, "bank-conflict swizzle assumes 4 chunk pairs per tile row");
+			uint32_t raw[2][2][2][4]; // [slice][row][k]
+#pragma unroll
+			for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+				for (int r = 0; r < 2; ++r) {
+#pragma unroll
+					for (int k = 0; k < 2; ++k) {
+						const uint4 v = *reinterpret_cast<const uint4*>(tile + ((2 * tz + sl) * TL::TY + (2 * ty + r)) * ROW_BYTES + (2 * tx + (k ^ sel)) * 16);
+						raw[sl][r][k][0] = v.x; raw[sl][r][k][1] = v.y; raw[sl][r][k][2] = v.z; raw[sl][r][k][3] = v.w;
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+			uint32_t l1[4];
+			if constexpr (!WIDE) {
+				uint32_t o0[2], o1[2];
+				reduce_rows_3d<EK, CH, 4>(raw[0][0][0], raw[0][1][0], raw[1][0][0], raw[1][1][0], o0, P.no_double);
+				reduce_rows_3d<EK, CH, 4>(raw[0][0][1], raw[0][1][1], raw[1][0][1], raw[1][1][1], o1, P.no_double);
+				l1[0] = sel ? o1[0] : o0[0]; l1[1] = sel ? o1[1] : o0[1];
+				l1[2] = sel ? o0[0] : o1[0]; l1[3] = sel ? o0[1] : o1[1];
+			} else {
+				uint32_t rr[2][2][8];
+#pragma unroll
+				for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+					for (int r = 0; r < 2; ++r)
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							rr[sl][r][i] = sel ? raw[sl][r][1][i] : raw[sl][r][0][i];
+							rr[sl][r][4 + i] = sel ? raw[sl][r][0][i] : raw[sl][r][1][i];
+						}
+				reduce_rows_3d<EK, CH, 8>(rr[0][0], rr[0][1], rr[1][0], rr[1][1], l1, P.no_double);
+			}
+			const uint32_t row = tile_y * (TL::TY / 2) + ty, slice = tile_z * (TL::TZ / 2) + tz;
+			const uint64_t l1_rows = P.dim[1] >> 1;
+			*reinterpret_cast<uint4*>(g1 + ((uint64_t)slice * l1_rows + row) * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
+				make_uint4(l1[0], l1[1], l1[2], l1[3]);
+			if (need_finish) {
+				if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+				*reinterpret_cast<uint4*>(buf_a + (tz * (TL::TY / 2) + ty) * (ROW_BYTES / 2) + tx * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+			}
 		}
-		const uint32_t row = tile_y * (TL::TY / 2) + ty, slice = tile_z * (TL::TZ / 2) + tz;
-		const uint64_t l1_rows = P.dim[1] >> 1;
-		*reinterpret_cast<uint4*>(g1 + ((uint64_t)slice * l1_rows + row) * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
-			make_uint4(l1[0], l1[1], l1[2], l1[3]);
-		*reinterpret_cast<uint4*>(buf_a + (tz * (TL::TY / 2) + ty) * (ROW_BYTES / 2) + tx * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+
+		// this warp's part of buf_a is written: hand the slot to the finisher pool (arrive = release)
+		if (need_finish) {
+			if (tid == 0) slot_tile[slot] = t; // only after this thread's wait on slot_empty above
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_full[slot]);
+		}
+
+		if (++s == stages) { s = 0; ++use; }
+		if (++slot == FLMIP_FINISHER_WARPS) { slot = 0; ++slot_use; }
 	}
-
-	__syncthreads();
-	if (tid >= 32) return;
-
-	// ---- warp 0: remaining levels of this tile ---------------------------------------------------------
-	constexpr uint32_t S0 = TL::IN_REG_LEVELS; // level held in buf_a
-	if (S0 >= P.level_count) return;
-	Region R;
-	R.lvl = S0;
-	R.w = TL::TX >> S0; R.h = TL::TY >> S0; R.d = (DIMS == 3 ? TL::TZ >> S0 : 1u);
-	R.ox = tile_x * R.w; R.oy = tile_y * R.h; R.oz = (DIMS == 3 ? tile_z * R.d : 0u);
-	uint8_t *src = buf_a, *dst = buf_b;
-	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
-	if (!next_level_has_texels<DIMS>(P, R.lvl)) return;
-
-	// ---- group stage: the last tile of a G x G (x G) tile group reduces the group's patch -----------------
-	constexpr uint32_t G = TL::GROUP;
-	const uint32_t gx = tile_x / G, gy = tile_y / G, gz = (DIMS == 3 ? tile_z / G : 0u);
-	const uint32_t ntx = min(G, P.tiles[0] - gx * G), nty = min(G, P.tiles[1] - gy * G), ntz = (DIMS == 3 ? min(G, P.tiles[2] - gz * G) : 1u);
-	const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
-	uint32_t* counters = reinterpret_cast<uint32_t*>(P.counters);
-	if (!arrive_last(counters + (uint64_t)layer * groups_per_layer + (gz * P.groups[1] + gy) * P.groups[0] + gx, ntx * nty * ntz, lane)) return;
-	// patch = this group's part of level R.lvl (R.w/h/d are the per-tile remainders here)
-	R.ox = gx * G * R.w; R.oy = gy * G * R.h; R.oz = gz * G * R.d;
-	R.w *= ntx; R.h *= nty; R.d *= ntz;
-	src = buf_a; dst = buf_b;
-	gather_region<BPP, DIMS>(src, R, P, layer, lane);
-	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
-	if (!next_level_has_texels<DIMS>(P, R.lvl)) return;
-
-	// ---- layer stage: the last group of a layer finishes the chain -----------------------------------------
-	if (!arrive_last(counters + (uint64_t)P.layers * groups_per_layer + layer, groups_per_layer, lane)) return;
-	R.ox = R.oy = R.oz = 0;
-	R.w = P.dim[0] >> R.lvl; R.h = P.dim[1] >> R.lvl; R.d = (DIMS == 3 ? P.dim[2] >> R.lvl : 1u);
-	src = buf_a; dst = buf_b;
-	gather_region<BPP, DIMS>(src, R, P, layer, lane);
-	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+	if (tid == 0) dbg_trace(P, 2);
+	// release the finisher pool: one sentinel per finisher warp in the next FLMIP_FINISHER_WARPS slots
+	if (need_finish) {
+		for (uint32_t k = 0; k < FLMIP_FINISHER_WARPS; ++k) {
+			if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+			if (tid == 0) slot_tile[slot] = FLMIP_NO_TILE;
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_full[slot]);
+			if (++slot == FLMIP_FINISHER_WARPS) { slot = 0; ++slot_use; }
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -651,7 +1028,7 @@ extern "C" __global__ void __launch_bounds__(256) flmip_fill(const __grid_consta
 }
 
 #define FLMIP_FAST_KERNEL(D, K, CHN)                                                                                            \
-	extern "C" __global__ void __launch_bounds__(256) flmip_fast##D##d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,    \
+	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_fast##D##d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,    \
 																					   const __grid_constant__ flmip_fast_params P) { \
 		fast_body<K, CHN, D>(tmap, P);                                                                                          \
 	}

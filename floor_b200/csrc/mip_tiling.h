@@ -34,7 +34,7 @@ template <int BPP, int DIMS> struct flmip_tiling {
 	static constexpr uint32_t THREADS_X = TILE_BYTES_X / 32u;       // 32 bytes (two 16-byte chunks) per thread and row
 	static constexpr uint32_t THREADS_Y = (DIMS == 2 ? TY / 4u : TY / 2u);
 	// levels produced in registers before the shared-memory cascade takes over
-	static constexpr uint32_t IN_REG_LEVELS = (DIMS == 2 && BPP < 16) ? 2u : 1u;
+	static constexpr uint32_t IN_REG_LEVELS = (DIMS == 2) ? 2u : 1u;
 	// levels one tile can finish on its own, and the texels of that level one tile holds
 	static constexpr uint32_t TILE_LEVELS = (DIMS == 2 ? (uint32_t)flmip_ilog2(TX < TY ? TX : TY) : (uint32_t)flmip_ilog2(flmip_min3(TX, TY, TZ)));
 	static constexpr uint32_t REM_TEXELS = (TX >> TILE_LEVELS) * (TY >> TILE_LEVELS) * (DIMS == 3 ? (TZ >> TILE_LEVELS) : 1u);
@@ -44,17 +44,19 @@ template <int BPP, int DIMS> struct flmip_tiling {
 		return (DIMS == 2 ? g * g : g * g * g) * REM_TEXELS * BPP <= CASCADE_BYTES ? g : group_for(g / 2);
 	}
 	static constexpr uint32_t GROUP = group_for(DIMS == 2 ? 16u : 8u); // tiles per group and dimension
-	static constexpr uint32_t SMEM_BYTES = TILE_BYTES + CASCADE_BYTES + CASCADE_BYTES / 4u;
+	// FLMIP_FINISHER_WARPS cascade slots (buf_a + buf_b each) + the CTA's patch buffer for the group / layer stages
+	static constexpr uint32_t CASCADE_SMEM_BYTES = (FLMIP_FINISHER_WARPS + 1u) * (CASCADE_BYTES + CASCADE_BYTES / 4u);
+	static constexpr uint32_t smem_bytes(uint32_t stages) { return stages * TILE_BYTES + CASCADE_SMEM_BYTES; }
 	static_assert(GROUP >= 2, "group patch does not fit");
 };
 
 // run-time view of the same numbers for the host planner
 struct flmip_tiling_rt {
-	uint32_t tx, ty, tz, tile_levels, group, cascade_bytes, smem_bytes, tile_bytes_x;
+	uint32_t tx, ty, tz, tile_levels, group, cascade_bytes, tile_bytes, cascade_smem_bytes, tile_bytes_x;
 };
 template <int BPP, int DIMS> constexpr flmip_tiling_rt flmip_tiling_make() {
 	using T = flmip_tiling<BPP, DIMS>;
-	return flmip_tiling_rt{ T::TX, T::TY, T::TZ, T::TILE_LEVELS, T::GROUP, T::CASCADE_BYTES, T::SMEM_BYTES, T::TILE_BYTES_X };
+	return flmip_tiling_rt{ T::TX, T::TY, T::TZ, T::TILE_LEVELS, T::GROUP, T::CASCADE_BYTES, T::TILE_BYTES, T::CASCADE_SMEM_BYTES, T::TILE_BYTES_X };
 }
 inline flmip_tiling_rt flmip_tiling_lookup(uint32_t bpp, uint32_t dims) {
 	if (dims == 2) {
