@@ -396,15 +396,12 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 
 	// counters: one per tile group and one per layer, zeroed once; the kernel resets what it uses
 	const uint64_t n_groups = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2];
-	const uint64_t n_column_words = n_groups * tl.group * FLMIP_COLUMN_COUNTER_STRIDE;
-	const uint64_t n_counters = n_groups + im.layers + 1000000u /* debug */ + n_column_words;
+	const uint64_t n_counters = n_groups + im.layers + 2u /* scheduler */;
 	CU_TRY(cu.p_cuMemAlloc(&im.counters, n_counters * sizeof(uint32_t)), "cuMemAlloc(counters)");
 	CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, nullptr), "cuMemsetD32Async(counters)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
 	P.counters = im.counters;
-	P.sched = im.counters + (n_groups + im.layers + 2u) * sizeof(uint32_t);
-	P.debug_off = (uint32_t)((n_groups + im.layers + 8u) / 2u);
-	P.column_counters = im.counters + (n_groups + im.layers + 1000000u) * sizeof(uint32_t);
+	P.sched = im.counters + (n_groups + im.layers) * sizeof(uint32_t);
 
 	// TMA descriptor over level 0: rank 3 in uint32 units -- (x, y, layer) for 2D / array / cube, (x, y, z) for volumes
 	const cuuint64_t row_bytes = (cuuint64_t)W * im.bpp;
@@ -418,7 +415,8 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 		   "cuTensorMapEncodeTiled");
 
 	// persistent launch shape: CTAs per SM x ring depth that fit the SM's shared memory (1 KiB is reserved per CTA).
-	// Defaults: 2 CTAs per SM, as many stages as fit (at most 4); FLMIP_CTAS_PER_SM / FLMIP_STAGES override for tuning.
+	// Defaults: 2 CTAs per SM x 2 stages (128 KiB of loads in flight per SM: more only adds queueing latency to every
+	// fence / atomic round trip of the finishers); FLMIP_CTAS_PER_SM / FLMIP_STAGES override for tuning.
 	auto env_u32 = [](const char* name, uint32_t def) {
 		const char* v = getenv(name);
 		return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : def;
@@ -429,12 +427,11 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	const uint32_t budget = per_cta < ds->smem_per_block_optin - 2048u ? per_cta : ds->smem_per_block_optin - 2048u;
 	if (budget < tl.cascade_smem_bytes + tl.tile_bytes) return fail(FLMIP_ERR_INVALID, "FLMIP_CTAS_PER_SM=%u leaves no room for a tile", ctas_per_sm);
 	uint32_t stages = (budget - tl.cascade_smem_bytes) / tl.tile_bytes;
-	const uint32_t want = env_u32("FLMIP_STAGES", 4);
+	const uint32_t want = env_u32("FLMIP_STAGES", 2);
 	if (stages > want) stages = want;
 	if (stages > FLMIP_MAX_STAGES) stages = FLMIP_MAX_STAGES;
 	if (stages < 1) stages = 1;
 	P.stages = stages;
-	P.debug_flags = env_u32("FLMIP_DEBUG_FLAGS", 0);
 	im.fast_smem = stages * tl.tile_bytes + tl.cascade_smem_bytes;
 	const uint64_t resident = (uint64_t)ds->info.units * ctas_per_sm;
 	im.fast_grid = (uint32_t)(P.total_units < resident ? P.total_units : resident);
@@ -786,13 +783,6 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 	return FLMIP_OK;
 }
 
-int flmip_debug_read(flmip_image img, uint64_t* out, uint32_t n) {
-	WITH_DEVICE(img->device)
-	cu.p_cuStreamSynchronize(nullptr);
-	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, img->counters + (uint64_t)img->fast_params.debug_off * 8u, n * 8u, nullptr), "dbg");
-	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "dbg");
-	return 0;
-}
 int flmip_mip_chain_generate(flmip_image img, flmip_stream stream) { return flmip_mip_chain_generate_from(img, 0, stream); }
 
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {

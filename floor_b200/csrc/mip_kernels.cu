@@ -351,7 +351,7 @@ __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Regio
 			reduce_texel<EK, CH, DIMS, false>(src + (size_t)(2 * z) * slice_pitch + (size_t)(2 * y) * row_pitch + (size_t)(2 * x) * BPP,
 											  row_pitch, slice_pitch, out, P.no_double);
 			IO::store(dst + (size_t)i * BPP, out);
-			if (!(P.debug_flags & 2u)) IO::store(gdst + ((uint64_t)(oz + z) * LH * LW + (uint64_t)(oy + y) * LW + (ox + x)) * BPP, out);
+			IO::store(gdst + ((uint64_t)(oz + z) * LH * LW + (uint64_t)(oy + y) * LW + (ox + x)) * BPP, out);
 		}
 		__syncwarp();
 		uint8_t* t = src; src = dst; dst = t;
@@ -453,19 +453,6 @@ __device__ __forceinline__ Region finish_tile(uint8_t* buf_a, uint8_t* buf_b, co
 	return R;
 }
 
-// debug trace: (type, cta, ns) records appended to the instrumentation area when debug flag 512 is set
-__device__ __forceinline__ void dbg_trace(const flmip_fast_params& P, uint32_t type, uint32_t extra = 0) {
-	if (!(P.debug_flags & 512u)) return;
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	unsigned long long* d = reinterpret_cast<unsigned long long*>(P.counters) + P.debug_off;
-	const unsigned long long idx = atomicAdd(d + 16, 1ull);
-	if (idx < 200000ull) {
-		d[32 + 2 * idx] = ((unsigned long long)type << 48) | ((unsigned long long)extra << 24) | blockIdx.x;
-		d[33 + 2 * idx] = t;
-	}
-}
-
 // Group bookkeeping of a unit: its group's counters and how many units the group has.
 template <int BPP, int DIMS> struct GroupOf {
 	using TL = flmip_tiling<BPP, DIMS>;
@@ -480,17 +467,10 @@ template <int BPP, int DIMS> struct GroupOf {
 		const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
 		return (uint64_t)layer * groups_per_layer + (gz * P.groups[1] + gy) * P.groups[0] + gx;
 	}
-	// Two-step arrival.  Tiles that are in flight at the same time are neighbours along x, and the L2 atomic unit
-	// serialises operations on one address: a tile first arrives on the counter of its COLUMN within the group
-	// (G counters per group, FLMIP_COLUMN_COUNTER_STRIDE words apart), the last tile of a column on the group counter.
-	__device__ __forceinline__ uint32_t* column_counter(const flmip_fast_params& P, uint32_t layer, uint32_t unit_x) const {
-		return reinterpret_cast<uint32_t*>(P.column_counters) + (index(P, layer) * G + (unit_x & (G - 1u))) * FLMIP_COLUMN_COUNTER_STRIDE;
-	}
-	__device__ __forceinline__ uint32_t column_tiles() const { return nty * ntz; }
 	__device__ __forceinline__ uint32_t* counter(const flmip_fast_params& P, uint32_t layer) const {
 		return reinterpret_cast<uint32_t*>(P.counters) + index(P, layer);
 	}
-	__device__ __forceinline__ uint32_t columns() const { return ntx; }
+	__device__ __forceinline__ uint32_t units() const { return ntx * nty * ntz; }
 };
 
 // Last arriver of a group of units: reduces the group's patch and, if its group is the last one of the layer, the rest of
@@ -505,54 +485,31 @@ __device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b,
 	const uint32_t layer = tc.layer;
 	const GroupOf<BPP, DIMS> grp(P, tc);
 
-	if (lane == 0) dbg_trace(P, 3);
-	unsigned long long dbg_t0 = 0, dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0;
-	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 	if (lane == 0) {
 		while (atomicCAS(patch_lock, 0u, 1u) != 0u) __nanosleep(64);
 	}
 	__syncwarp();
-	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
-	if (lane == 0) dbg_trace(P, 7);
 	// patch = this group's part of the level the units ended on (R.w/h/d are the per-unit remainders here)
 	R.ox = grp.gx * G * R.w; R.oy = grp.gy * G * R.h; R.oz = grp.gz * G * R.d;
 	R.w *= grp.ntx; R.h *= grp.nty; R.d *= grp.ntz;
 	uint8_t *src = patch_a, *dst = patch_b;
-	if (!(P.debug_flags & 128u)) gather_region<BPP, DIMS>(src, R, P, layer, lane);
-	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t2));
-	if (lane == 0) dbg_trace(P, 8);
-	if (!(P.debug_flags & 256u)) cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
-	if (P.debug_flags & 64u) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t3));
-	if (lane == 0) dbg_trace(P, 9);
+	gather_region<BPP, DIMS>(src, R, P, layer, lane);
+	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
 
 	// ---- layer stage: the last group of a layer finishes the chain -----------------------------------------
 	const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
 	if (next_level_has_texels<DIMS>(P, R.lvl) &&
 		arrive_last(reinterpret_cast<uint32_t*>(P.counters) + (uint64_t)P.layers * groups_per_layer + layer, groups_per_layer, lane)) {
-		if (lane == 0) dbg_trace(P, 10);
 		R.ox = R.oy = R.oz = 0;
 		R.w = P.dim[0] >> R.lvl; R.h = P.dim[1] >> R.lvl; R.d = (DIMS == 3 ? P.dim[2] >> R.lvl : 1u);
 		src = patch_a; dst = patch_b;
 		gather_region<BPP, DIMS>(src, R, P, layer, lane);
-		if (lane == 0) dbg_trace(P, 11);
 		cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
 	}
 	__syncwarp();
 	if (lane == 0) {
 		__threadfence_block();
 		atomicExch(patch_lock, 0u);
-	}
-	if (lane == 0) dbg_trace(P, 4);
-	if ((P.debug_flags & 64u) && lane == 0) {
-		unsigned long long dbg_t4;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t4));
-		unsigned long long* d = reinterpret_cast<unsigned long long*>(P.counters) + P.debug_off;
-		atomicAdd(d + 0, 1ull);
-		atomicAdd(d + 1, dbg_t1 - dbg_t0); // lock
-		atomicAdd(d + 2, dbg_t2 - dbg_t1); // gather
-		atomicAdd(d + 3, dbg_t3 - dbg_t2); // cascade
-		atomicAdd(d + 4, dbg_t4 - dbg_t3); // layer stage + unlock
-		atomicMax(d + 5, dbg_t4 - dbg_t0);
 	}
 }
 
@@ -602,7 +559,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 
 	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
 	// the finisher pool is idle when the consumers' in-register levels end the chain
-	const bool need_finish = P.level_count > TL::IN_REG_LEVELS + 1u && !(P.debug_flags & 1u);
+	const bool need_finish = P.level_count > TL::IN_REG_LEVELS + 1u;
 	if (warp >= FLMIP_FINISHER_WARP0) {
 		// ---- finishers: a pool of warps that take the CTA's tiles in ring order by ticket ---------------------
 		if (!need_finish) return; // the consumers produce every level
@@ -620,10 +577,8 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			const uint32_t t = slot_tile[slot];
 			if (t == FLMIP_NO_TILE) break; // the consumers are done: one sentinel per finisher warp
 			const TileCoord tc = tile_coord<DIMS>(P, t);
-			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 12, n);
 			uint8_t* rem = nullptr;
 			Region R = finish_tile<EK, CH, DIMS>(buf_a, buf_a + TL::CASCADE_BYTES, P, tc, lane, rem);
-			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 13, n);
 			bool carry_on = next_level_has_texels<DIMS>(P, R.lvl);
 			if (carry_on && kbits != 0) {
 				// ---- unit stage: the remainders of the unit's tiles meet in shared memory; whoever brings the last one
@@ -663,9 +618,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			if (!carry_on) continue;
 			// publish the unit; the last arriver of its group carries on
 			const GroupOf<BPP, DIMS> grp(P, tc);
-			const bool last = arrive_last(grp.column_counter(P, tc.layer, tc.ux), grp.column_tiles(), lane) && arrive_last(grp.counter(P, tc.layer), grp.columns(), lane);
-			if (lane == 0 && (n & 7u) == 0) dbg_trace(P, 14, n);
-			if (last) finish_group<EK, CH, DIMS>(patch_a, patch_b, &patch_lock, P, tc, R, lane);
+			if (arrive_last(grp.counter(P, tc.layer), grp.units(), lane)) finish_group<EK, CH, DIMS>(patch_a, patch_b, &patch_lock, P, tc, R, lane);
 		}
 		return;
 	}
@@ -676,15 +629,17 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		// flight, lane (it % PF) holds the tile of iteration `it`.
 		constexpr uint32_t PF = FLMIP_SCHED_PREFETCH;
 		uint32_t* const sched = reinterpret_cast<uint32_t*>(P.sched);
+		// The first unit of a CTA is its own index (no round trip before the first load); the counter hands out the rest.
 		uint32_t pf = FLMIP_NO_TILE;
-		if (lane < PF) pf = atomicAdd(&sched[0], 1u);
+		if (lane == 0) pf = blockIdx.x;
+		else if (lane < PF) pf = gridDim.x + atomicAdd(&sched[0], 1u);
 		uint32_t s = 0, use = 0, dead = 0;
 		const uint32_t kbits = P.unit_shift * DIMS;
 		for (uint32_t it = 0; dead < PF; ++it) {
 			const uint32_t u = __shfl_sync(0xFFFFFFFFu, pf, it % PF);
 			if (u >= P.total_units) { ++dead; continue; } // this lane ran off the end; the others may still hold units
 			dead = 0;
-			if (lane == it % PF) pf = atomicAdd(&sched[0], 1u); // unit of iteration it + PF
+			if (lane == it % PF) pf = gridDim.x + atomicAdd(&sched[0], 1u); // unit of iteration it + PF
 			if (lane == 0) {
 				for (uint32_t k = 0; k < (1u << kbits); ++k) {
 					const uint32_t t = (u << kbits) | k;
@@ -726,12 +681,10 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 	// different tiles.
 	const uint32_t sel = (lane >> 2) & 1u; // quarter-warps read conflict-free by swapping the chunk order on lane bit 2
 	uint32_t s = 0, use = 0, slot = 0, slot_use = 0;
-	if (tid == 0) dbg_trace(P, 1);
 	for (uint32_t it = 0;; ++it) {
 		mbar_wait(&full_bar[s], use & 1u);
 		const uint32_t t = stage_tile[s];
 		if (t == FLMIP_NO_TILE) break;
-		if (tid == 0 && (it & 7u) == 0) dbg_trace(P, 5, it);
 		const TileCoord tc = tile_coord<DIMS>(P, t);
 		const uint32_t tile_x = tc.x, tile_y = tc.y, tile_z = tc.z, layer = tc.layer;
 		const uint8_t* const tile = smem_raw + (size_t)s * TL::TILE_BYTES;
@@ -885,7 +838,6 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		if (++s == stages) { s = 0; ++use; }
 		if (++slot == FLMIP_FINISHER_WARPS) { slot = 0; ++slot_use; }
 	}
-	if (tid == 0) dbg_trace(P, 2);
 	// release the finisher pool: one sentinel per finisher warp in the next FLMIP_FINISHER_WARPS slots
 	if (need_finish) {
 		for (uint32_t k = 0; k < FLMIP_FINISHER_WARPS; ++k) {

@@ -8,7 +8,6 @@
 // persistent single-pass CTA = 8 consumer warps + 1 TMA producer warp + FLMIP_FINISHER_WARPS finisher warps
 #define FLMIP_FINISHER_WARPS 4
 #define FLMIP_SCHED_PREFETCH 4u   // tile-index fetches the producer keeps in flight
-#define FLMIP_COLUMN_COUNTER_STRIDE 8u // words between two column counters (one 32-byte sector each)
 #define FLMIP_UNIT_PATCH_BYTES 512u    // remainders of the tiles of one unit: at most 8 x (1 x 2 x 2 texels of 16 bytes)
 #define FLMIP_NO_TILE 0xFFFFFFFFu // end-of-work sentinel in the tile ring / cascade slots
 #define FLMIP_BLOCK_THREADS ((8 + 1 + FLMIP_FINISHER_WARPS) * 32)
@@ -49,7 +48,6 @@ struct flmip_fast_params {
 	uint64_t base;
 	uint64_t level_off[FLMIP_MAX_LEVELS];
 	uint64_t counters;  // uint32[layers * groups] group counters, then uint32[layers] layer counters
-	uint64_t column_counters; // uint32[layers * groups * GROUP * FLMIP_COLUMN_COUNTER_STRIDE]: first step of a tile's arrival
 	uint64_t sched;     // uint32[2]: next tile to hand out, producers done (both left at zero by the kernel)
 	uint32_t dim[3];    // level-0 size in texels (z = 1 for 2D)
 	uint32_t tiles[3];  // tiles per layer
@@ -60,8 +58,6 @@ struct flmip_fast_params {
 	uint32_t layers, level_count, no_double;
 	uint32_t total_units;   // units per layer * layers, handed out by the dynamic scheduler
 	uint32_t stages;        // depth of the TMA tile ring in shared memory (<= FLMIP_MAX_STAGES)
-	uint32_t debug_off;     // debug: index (in u64) of the instrumentation area inside `counters`
-	uint32_t debug_flags;   // TIMING EXPERIMENTS ONLY (results become wrong): 1 = skip every level beyond the in-register ones
 };
 
 struct flmip_fill_params {

@@ -8,12 +8,12 @@ for dbg in $1; do
     extra=""
     [ $w = c3 ] && extra="--layers 256"
     [ $w = c4 ] && extra="--layers 4"
-    r=$(FLMIP_DEBUG_FLAGS=$dbg timeout 300 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --no-e2e $extra 2>&1 | python -c "
+    r=$(timeout 300 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --no-e2e $extra 2>&1 | python -c "
 import sys,json
 try:
   d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['roofline']['frac'])
 except Exception as e: print('ERR', e)
 ")
-    echo "dbg=$dbg ${FLMIP_CTAS_PER_SM:-} ${FLMIP_STAGES:-} $w $r" | tee -a gpurun_out/exp.txt
+    echo "${FLMIP_CTAS_PER_SM:-} ${FLMIP_STAGES:-} $w $r" | tee -a gpurun_out/exp.txt
   done
 done

@@ -2,10 +2,10 @@
 # tuning sweep of the persistent single-pass kernel: CTAs per SM x ring depth, per workload
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
+
+
 : > gpurun_out/sweep.txt
-for cfg in "2 3" "2 2" "3 2" "1 6" "4 1"; do
+for cfg in "2 3" "2 2" "2 1" "1 6" "1 4"; do
   set -- $cfg
   for w in c2 c5 c3 c4; do
     extra=""
