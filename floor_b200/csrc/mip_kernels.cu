@@ -70,15 +70,24 @@ template <uint32_t EK> struct Codec {
 		}
 	}
 
+	// 0x4B000000 held in a register the compiler cannot see through: PRMT has one immediate slot, and it must go to
+	// the (compile-time) selector -- with the constant as the immediate every PRMT needs a MOV for its selector.
+	// (ptxas folds a constant mov, so the value is derived from a special register it cannot reason about.)
+	static __device__ __forceinline__ uint32_t magic_bits() {
+		uint32_t r;
+		asm("{\n\t.reg .u32 t;\n\tmov.u32 t, %%nsmid;\n\tshr.u32 t, t, 31;\n\tor.b32 %0, t, 0x4B000000;\n\t}" : "=r"(r));
+		return r;
+	}
+
 	// decode element i of a row of packed 32-bit words
 	static __device__ __forceinline__ uint32_t dec_at(const uint32_t* w, int i) {
 		if constexpr (EK == FLMIP_EK_UNORM8) {
 			// one PRMT builds 0x4B0000uu
-			return __float_as_uint(__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7440u | (uint32_t)(i & 3))), UNORM_C,
+			return __float_as_uint(__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 2], magic_bits(), 0x7440u | (uint32_t)(i & 3))), UNORM_C,
 											 -(MAGIC * UNORM_C)));
 		} else if constexpr (EK == FLMIP_EK_UNORM16) {
 			return __float_as_uint(
-				__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 1], 0x4B000000u, (i & 1) ? 0x7432u : 0x7410u)), UNORM_C, -(MAGIC * UNORM_C)));
+				__fmaf_rn(__uint_as_float(__byte_perm(w[i >> 1], magic_bits(), (i & 1) ? 0x7432u : 0x7410u)), UNORM_C, -(MAGIC * UNORM_C)));
 		} else if constexpr (EK == FLMIP_EK_F16) {
 			const __half2 h = *reinterpret_cast<const __half2*>(&w[i >> 1]);
 			return __float_as_uint((i & 1) ? __high2float(h) : __low2float(h));
@@ -88,18 +97,21 @@ template <uint32_t EK> struct Codec {
 	}
 
 	// encode back to storage bits: host_image.hpp:672-722 + insert_channels :391-460 (truncating), :801-825
-	static __device__ __forceinline__ uint32_t enc(uint32_t v, uint32_t no_double) {
+	static __device__ __forceinline__ uint32_t enc(uint32_t v, uint32_t no_double) { return enc_dirty(v, no_double) & MASK; }
+
+	// same, but bits above the storage width are unspecified (the packers select bytes with PRMT anyway)
+	static __device__ __forceinline__ uint32_t enc_dirty(uint32_t v, uint32_t no_double) {
 		if constexpr (EK == FLMIP_EK_F32 || EK == FLMIP_EK_U32 || EK == FLMIP_EK_I32) {
 			return v;
 		} else if constexpr (IS_INT) {
-			return v & MASK;
+			return v;
 		} else if constexpr (EK == FLMIP_EK_F16) {
 			return (uint32_t)__half_as_ushort(__float2half_rn(__uint_as_float(v)));
 		} else if constexpr (EK == FLMIP_EK_UNORM8) {
 			// v in [0, 1] -> t in [0, 255]: trunc(t) sits in the low mantissa byte of t + 2^23 (RZ)
-			return __float_as_uint(__fadd_rz(__fmul_rn(__uint_as_float(v), 255.0f), MAGIC)) & 0xFFu;
+			return __float_as_uint(__fadd_rz(__fmul_rn(__uint_as_float(v), 255.0f), MAGIC));
 		} else if constexpr (EK == FLMIP_EK_SNORM8) {
-			return (uint32_t)__float2int_rz(__fmul_rn(__uint_as_float(v), 127.0f)) & 0xFFu;
+			return (uint32_t)__float2int_rz(__fmul_rn(__uint_as_float(v), 127.0f));
 		} else {
 			// 9..16 bit normalized: fp_scale_type is double unless FLOOR_DEVICE_NO_DOUBLE (host_image.hpp:398-402).
 			// double(f) * scale is exact (24 + 16 significant bits), so the reference computes trunc(f * scale) of the
@@ -108,8 +120,8 @@ template <uint32_t EK> struct Codec {
 			constexpr float scale = (EK == FLMIP_EK_UNORM16 ? 65535.0f : 32767.0f);
 			const float f = __uint_as_float(v);
 			const float t = no_double ? __fmul_rn(f, scale) : __fmul_rz(f, scale);
-			if constexpr (EK == FLMIP_EK_UNORM16) return __float_as_uint(__fadd_rz(t, MAGIC)) & 0xFFFFu;
-			else return (uint32_t)__float2int_rz(t) & 0xFFFFu;
+			if constexpr (EK == FLMIP_EK_UNORM16) return __float_as_uint(__fadd_rz(t, MAGIC));
+			else return (uint32_t)__float2int_rz(t);
 		}
 	}
 
@@ -126,14 +138,14 @@ template <uint32_t EK> struct Codec {
 					const __half2 h = __floats2half2_rn(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
 					out[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
 				} else {
-					out[i >> 1] = __byte_perm(enc(v[i], no_double), enc(v[i + 1], no_double), 0x5410u);
+					out[i >> 1] = __byte_perm(enc_dirty(v[i], no_double), enc_dirty(v[i + 1], no_double), 0x5410u);
 				}
 			}
 		} else {
 #pragma unroll
 			for (int i = 0; i < N; i += 4) {
-				const uint32_t lo = __byte_perm(enc(v[i], no_double), enc(v[i + 1], no_double), 0x0040u);
-				const uint32_t hi = __byte_perm(enc(v[i + 2], no_double), enc(v[i + 3], no_double), 0x0040u);
+				const uint32_t lo = __byte_perm(enc_dirty(v[i], no_double), enc_dirty(v[i + 1], no_double), 0x0040u);
+				const uint32_t hi = __byte_perm(enc_dirty(v[i + 2], no_double), enc_dirty(v[i + 3], no_double), 0x0040u);
 				out[i >> 2] = __byte_perm(lo, hi, 0x5410u);
 			}
 		}

@@ -27,7 +27,9 @@ for rep in sys.argv[1:]:
             if w in hdr:
                 print(f"  {w:90s} {r[hdr.index(w)]} {units[hdr.index(w)]}")
         try:
-            rd = float(r[hdr.index("dram__bytes_read.sum")]); wr = float(r[hdr.index("dram__bytes_write.sum")])
-            print(f"  traffic (dram read + write, units as above)                                              {rd + wr:.3f}")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            total = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            print(f"  traffic = dram__bytes_read.sum + dram__bytes_write.sum                                      {total / 1e6:.3f} Mbyte")
         except Exception:
             pass
