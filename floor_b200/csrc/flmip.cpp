@@ -355,7 +355,9 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	// units of 2 x 2 (x 2) tiles when every dim has at least two tiles and there are enough tiles to keep every
 	// resident CTA busy with whole units (small images stay latency-bound: one tile per CTA then)
 	const uint64_t all_tiles = (uint64_t)P.tiles[0] * P.tiles[1] * P.tiles[2] * im.layers;
-	P.unit_shift = (P.tiles[0] >= 2 && P.tiles[1] >= 2 && (!is3d || P.tiles[2] >= 2) && (all_tiles >> im.dc) >= 2ull * ds->info.units) ? 1u : 0u;
+	const bool units_possible = P.tiles[0] >= 2 && P.tiles[1] >= 2 && (!is3d || P.tiles[2] >= 2);
+	const bool units_wanted = (flags & FLMIP_IMAGE_UNITS_ALWAYS) || (!(flags & FLMIP_IMAGE_UNITS_NEVER) && (all_tiles >> im.dc) >= 2ull * ds->info.units);
+	P.unit_shift = (units_possible && units_wanted) ? 1u : 0u;
 	for (int i = 0; i < 3; ++i) {
 		P.units[i] = (i == 2 && !is3d) ? 1u : P.tiles[i] >> P.unit_shift;
 		P.unit_cshift[i] = (uint32_t)flmip_ilog2(P.units[i]);

@@ -144,8 +144,8 @@ class device_queue:
 class device_image:
     def __init__(self, cqueue: device_queue, image_dim, image_type: int, data=None,
                  flags: int = MEMORY_FLAG.HOST_READ_WRITE, mip_level_limit: int = 0, no_double: bool = False,
-                 force_generic: bool = False):
-        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, LevelInfo
+                 force_generic: bool = False, units: bool | None = None):
+        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, LevelInfo
         self.dev = cqueue.dev
         dim = list(image_dim) + [0] * (4 - len(image_dim))
         # device_image::handle_image_type (device_image.hpp:70-91)
@@ -154,6 +154,7 @@ class device_image:
         self.image_dim = tuple(dim)
         self._handle = ctypes.c_void_p()
         cflags = (IMAGE_NO_DOUBLE if no_double else 0) | (IMAGE_FORCE_GENERIC if force_generic else 0)
+        cflags |= 0 if units is None else (IMAGE_UNITS_ALWAYS if units else IMAGE_UNITS_NEVER)
         _check(_L().flmip_image_create(self.dev.index, image_type, _u32x(dim, 4), mip_level_limit, cflags,
                                        ctypes.byref(self._handle)))
         n = ctypes.c_uint32()

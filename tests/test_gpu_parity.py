@@ -51,9 +51,11 @@ def test_single_pass_2d_all_formats(gpu_ctx, oracle_mod, fmt):
     for dim in [(w, 256), (w * 2, 128), (512 // bpp, 64)]:
         t = T.IMAGE_2D | fmt | M
         l0 = oracle_mod.fill_synthetic(dim, t, 100 + (fmt & 0xFFFF))
-        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
-        assert plan["single_pass"], (hex(t), dim, plan)
-        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "single-pass 2D")
+        want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8)
+        for units in (False, True):  # single tiles, and 2x2-tile units where the tile grid allows it
+            got, plan = gpu_chain(gpu_ctx, l0, dim, t, units=units)
+            assert plan["single_pass"], (hex(t), dim, plan)
+            assert_same(got, want, t, dim, f"single-pass 2D units={units}")
 
 
 @pytest.mark.parametrize("fmt", ALL_FORMATS)
@@ -62,9 +64,11 @@ def test_single_pass_3d_all_formats(gpu_ctx, oracle_mod, fmt):
     for dim in [(2 * 128 // bpp if bpp < 16 else 32, 32, 32), (128 // bpp if bpp < 16 else 8, 16, 64)]:
         t = T.IMAGE_3D | fmt | M
         l0 = oracle_mod.fill_synthetic(dim, t, 200 + (fmt & 0xFFFF))
-        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
-        assert plan["single_pass"], (hex(t), dim, plan)
-        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "single-pass 3D")
+        want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8)
+        for units in (False, True):
+            got, plan = gpu_chain(gpu_ctx, l0, dim, t, units=units)
+            assert plan["single_pass"], (hex(t), dim, plan)
+            assert_same(got, want, t, dim, f"single-pass 3D units={units}")
 
 
 @pytest.mark.parametrize("fmt", ALL_FORMATS)
@@ -100,6 +104,57 @@ def test_layered_and_cube(gpu_ctx, oracle_mod):
         got, plan = gpu_chain(gpu_ctx, l0, dim, t)
         assert plan["single_pass"] and plan["launches"] == 1, plan
         assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8), t, dim, "layered")
+
+
+def test_layered_with_units(gpu_ctx, oracle_mod):
+    """2x2-tile units on layered / cube images with several groups per layer"""
+    for bt, dim in [(T.IMAGE_2D_ARRAY | T.RGBA8, (1024, 1024, 5)), (T.IMAGE_CUBE_ARRAY | T.RGBA32F, (512, 512, 2)), (T.IMAGE_2D_ARRAY | T.R16F, (2048, 512, 3)),
+                    (T.IMAGE_3D | T.RGBA8, (256, 256, 256)), (T.IMAGE_2D | T.RG16, (4096, 2048))]:
+        t = bt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 17)
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t, units=True)
+        assert plan["single_pass"] and plan["launches"] == 1, plan
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=16), t, dim, "layered units")
+
+
+def test_baseline_configs_full_size(gpu_ctx, oracle_mod):
+    """BASELINE.json configs at full size where one image fits the oracle's budget: C1, C2, C5 against the oracle on every level;
+    C3 / C4 on a contiguous shard of layers / one cube (layers are independent; the oracle runs per layer anyway)"""
+    ctx, dev, q = gpu_ctx
+    cases = [(1, (1024, 1024), T.IMAGE_2D | T.RGBA8), (2, (8192, 8192), T.IMAGE_2D | T.RGBA16F), (5, (512, 512, 512), T.IMAGE_3D | T.R32F),
+             (3, (1024, 1024, 32), T.IMAGE_2D_ARRAY | T.RGBA8), (4, (4096, 4096, 1), T.IMAGE_CUBE_ARRAY | T.RGBA32F)]
+    for cid, dim, bt in cases:
+        t = bt | M
+        img = ctx.create_image(q, dim, t)
+        img.fill_synthetic(q, cid, layer_id0=7)
+        img.generate_mip_map_chain(q)
+        got = img.download_levels(q)
+        plan = img.plan()
+        img.destroy()
+        assert plan["single_pass"] and plan["launches"] == 1, (cid, plan)
+        l0 = got[: oracle_mod.level_size(dim, t, 0)]
+        assert np.array_equal(l0, oracle_mod.fill_synthetic(dim, t, cid, layer_id0=7)), cid  # device fill == oracle fill
+        want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=os.cpu_count() or 8)
+        assert hashlib.sha256(got.tobytes()).digest() == hashlib.sha256(want.tobytes()).digest(), f"config {cid}: GPU chain differs from the oracle"
+        del got, want, l0
+
+
+def test_top_level_is_the_mean_of_means_property(gpu_ctx, oracle_mod):
+    """size-independent property at full size: for a constant image every level is that constant (fp16 / fp32 exactly; unorm8 exactly,
+    cf. the constant-image KATs of the oracle tests)"""
+    ctx, dev, q = gpu_ctx
+    for dim, bt, dt, val in [((8192, 8192), T.IMAGE_2D | T.RGBA16F, np.float16, 0.3330078125), ((512, 512, 512), T.IMAGE_3D | T.R32F, np.float32, 1.2345678),
+                             ((1024, 1024, 16), T.IMAGE_2D_ARRAY | T.RGBA8, np.uint8, 77)]:
+        t = bt | M
+        img = ctx.create_image(q, dim, t)
+        n0 = img.levels[0]["size"] // np.dtype(dt).itemsize
+        host = np.full(n0, val, dtype=dt)
+        img.upload_levels(q, host, 0, 0)
+        img.generate_mip_map_chain(q)
+        got = img.download_levels(q).view(dt)
+        img.destroy()
+        assert np.all(got == np.array(val, dtype=dt)), (dim, hex(t))
+        del host, got
 
 
 def test_non_square_and_level_limit(gpu_ctx, oracle_mod):
