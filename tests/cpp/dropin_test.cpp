@@ -1,0 +1,135 @@
+// Test of the C++ drop-in (include/floor_b200/floor_b200.hpp) written the way a libfloor application uses the
+// reference API: cuda_context -> device -> queue -> create_image(GENERATE_MIP_MAPS) -> write / map / unmap.
+// The oracle (oracle/liboracle_minify.so, dlopen'd) is the checker.  TEST CODE: lives under tests/.
+//
+//   dropin_test --cpu   : enum / size arithmetic checks, the context reports "not supported" without a GPU
+//   dropin_test <oracle.so> : full parity run on GPU 0
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "floor_b200/floor_b200.hpp"
+
+using namespace fl;
+
+typedef int (*flo_generate_fn)(void*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t);
+typedef void (*flo_fill_fn)(void*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint32_t);
+
+static int failures = 0;
+#define CHECK(cond)                                                        \
+	do {                                                                   \
+		if (!(cond)) {                                                     \
+			std::fprintf(stderr, "CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+			++failures;                                                    \
+		}                                                                  \
+	} while (0)
+
+static void cpu_checks() {
+	constexpr auto t2 = IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA16F | IMAGE_TYPE::FLAG_MIPMAPPED | IMAGE_TYPE::READ_WRITE;
+	static_assert(image_type_bits(t2) == 0x802FC12ull);
+	CHECK(image_mip_level_count({ 8192, 8192, 0, 0 }, t2) == 14);
+	CHECK(image_bytes_per_pixel(t2) == 8);
+	CHECK(image_data_size_from_types({ 8192, 8192, 0, 0 }, t2) == 715827880ull);
+	CHECK(image_data_size_from_types({ 8192, 8192, 0, 0 }, t2, true) == 536870912ull);
+	CHECK(image_mip_level_data_offset_from_types({ 8192, 8192, 0, 0 }, t2, 1) == 536870912ull);
+	constexpr auto tc = IMAGE_TYPE::IMAGE_CUBE_ARRAY | IMAGE_TYPE::RGBA32F | IMAGE_TYPE::FLAG_MIPMAPPED;
+	CHECK(image_layer_count({ 4096, 4096, 64, 0 }, tc) == 384);
+	CHECK(image_data_size_from_types({ 4096, 4096, 64, 0 }, tc) == 137438951424ull);
+	// zero-dim quirk: 64x4 has 7 levels, levels 3.. are empty (image_types.hpp:751-766)
+	constexpr auto tq = IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::R8 | IMAGE_TYPE::FLAG_MIPMAPPED;
+	CHECK(image_mip_level_count({ 64, 4, 0, 0 }, tq) == 7);
+	CHECK(image_mip_level_data_size_from_types({ 64, 4, 0, 0 }, tq, 3) == 0);
+	CHECK(device_image::infer_rw_flags(IMAGE_TYPE::READ, MEMORY_FLAG::GENERATE_MIP_MAPS) == (MEMORY_FLAG::GENERATE_MIP_MAPS | MEMORY_FLAG::READ_WRITE));
+	CHECK(has_flag<IMAGE_TYPE::WRITE>(device_image::handle_image_type({ 64, 64, 0, 0 }, tq | IMAGE_TYPE::READ, MEMORY_FLAG::READ | MEMORY_FLAG::GENERATE_MIP_MAPS)));
+	CHECK(!has_flag<IMAGE_TYPE::FLAG_MIPMAPPED>(device_image::handle_image_type({ 1, 1, 0, 0 }, tq, MEMORY_FLAG::READ_WRITE)));
+}
+
+int main(int argc, char** argv) {
+	cpu_checks();
+	cuda_context ctx;
+	if (argc > 1 && !std::strcmp(argv[1], "--cpu")) {
+		if (!ctx.is_supported()) {
+			CHECK(ctx.get_devices().empty());
+			CHECK(ctx.get_device(device::TYPE::FASTEST_GPU) == nullptr);
+			std::printf("dropin_test --cpu: no CUDA device, context reports unsupported (no CPU fallback)\n");
+		}
+		std::printf("dropin_test --cpu: %s\n", failures ? "FAILED" : "ok");
+		return failures ? 1 : 0;
+	}
+	if (!ctx.is_supported()) {
+		std::fprintf(stderr, "dropin_test: CUDA is required\n");
+		return 2;
+	}
+	void* oracle = dlopen(argc > 1 ? argv[1] : "oracle/liboracle_minify.so", RTLD_NOW);
+	if (!oracle) {
+		std::fprintf(stderr, "dropin_test: cannot load the oracle: %s\n", dlerror());
+		return 2;
+	}
+	const auto flo_generate = (flo_generate_fn)dlsym(oracle, "flo_generate_mip_map_chain");
+	const auto flo_fill = (flo_fill_fn)dlsym(oracle, "flo_fill_synthetic");
+
+	const device* dev = ctx.get_device(device::TYPE::FASTEST_GPU);
+	auto queue = ctx.create_queue(*dev);
+	std::printf("device: %s (%u SMs, sm_%u%u)\n", dev->name.c_str(), dev->units, static_cast<const cuda_device*>(dev)->sm.x, static_cast<const cuda_device*>(dev)->sm.y);
+
+	struct Case { uint4 dim; IMAGE_TYPE type; };
+	const Case cases[] = {
+		{ { 1024, 1024, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA8 },          // BASELINE configs[0]
+		{ { 2048, 1024, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA16F },
+		{ { 256, 256, 5, 0 }, IMAGE_TYPE::IMAGE_2D_ARRAY | IMAGE_TYPE::RGBA8 },
+		{ { 128, 128, 2, 0 }, IMAGE_TYPE::IMAGE_CUBE_ARRAY | IMAGE_TYPE::RGBA32F },
+		{ { 128, 64, 64, 0 }, IMAGE_TYPE::IMAGE_3D | IMAGE_TYPE::R32F },
+		{ { 100, 37, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA16 },            // NPOT -> general kernel
+	};
+	for (const auto& c : cases) {
+		const IMAGE_TYPE type = c.type | IMAGE_TYPE::FLAG_MIPMAPPED | IMAGE_TYPE::READ;
+		const uint32_t dim[4] = { c.dim.x, c.dim.y, c.dim.z, c.dim.w };
+		const size_t l0_size = image_data_size_from_types(c.dim, type, true), all_size = image_data_size_from_types(c.dim, type);
+		std::vector<uint8_t> want(all_size), got(all_size), l0(l0_size);
+		flo_fill(l0.data(), dim, image_type_bits(type), 9, 0, image_layer_count(c.dim, type));
+		std::memcpy(want.data(), l0.data(), l0_size);
+		CHECK(flo_generate(want.data(), dim, image_type_bits(type | IMAGE_TYPE::WRITE), 0, 0, 8) == 0);
+
+		// ctor upload -> chain (GENERATE_MIP_MAPS), then look at every level
+		auto img = ctx.create_image(*queue, c.dim, type, l0, MEMORY_FLAG::READ | MEMORY_FLAG::HOST_READ_WRITE | MEMORY_FLAG::GENERATE_MIP_MAPS);
+		CHECK(img != nullptr);
+		if (!img) continue;
+		CHECK(img->get_generate_mip_maps() && img->get_image_data_size() == l0_size);
+		CHECK(img->get_mip_level_count() == image_mip_level_count(c.dim, type) && img->get_layer_count() == image_layer_count(c.dim, type));
+		CHECK(img->read_levels(*queue, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
+		CHECK(got == want);
+
+		// map -> modify -> unmap regenerates the chain
+		auto* mapped = static_cast<uint8_t*>(img->map(*queue));
+		CHECK(mapped != nullptr && std::memcmp(mapped, l0.data(), l0_size) == 0);
+		for (size_t i = 0; i < l0_size; ++i) mapped[i] = uint8_t(mapped[i] ^ 0x5A);
+		std::vector<uint8_t> l0b(mapped, mapped + l0_size);
+		CHECK(img->unmap(*queue, mapped));
+		std::memcpy(want.data(), l0b.data(), l0_size);
+		CHECK(flo_generate(want.data(), dim, image_type_bits(type | IMAGE_TYPE::WRITE), 0, 0, 8) == 0);
+		CHECK(img->read_levels(*queue, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
+		CHECK(got == want);
+
+		// write() of the whole level 0 regenerates too; an out-of-bounds write is rejected with false
+		const uint3 extent { c.dim.x, image_dim_count(type) >= 2 ? c.dim.y : 1u, image_dim_count(type) >= 3 ? c.dim.z : 1u };
+		CHECK(img->write(*queue, l0.data(), l0.size(), { 0, 0, 0 }, extent, { 0, 0 }, { 0, img->get_layer_count() - 1 }));
+		std::memcpy(want.data(), l0.data(), l0_size);
+		CHECK(flo_generate(want.data(), dim, image_type_bits(type | IMAGE_TYPE::WRITE), 0, 0, 8) == 0);
+		CHECK(img->read_levels(*queue, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
+		CHECK(got == want);
+		CHECK(!img->write(*queue, l0.data(), l0.size(), { 1, 0, 0 }, extent, { 0, 0 }, { 0, 0 }));
+	}
+	// constructor invariants throw (device_image.hpp:502-539); unsupported formats return nullptr (cuda_image.cpp:173-180)
+	bool threw = false;
+	try {
+		ctx.create_image(*queue, { 64, 64, 0, 0 }, IMAGE_TYPE::IMAGE_2D_MSAA | IMAGE_TYPE::RGBA8 | IMAGE_TYPE::FLAG_MIPMAPPED);
+	} catch (const std::runtime_error&) { threw = true; }
+	CHECK(threw);
+	CHECK(ctx.create_image(*queue, { 64, 64, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGB8 | IMAGE_TYPE::FLAG_MIPMAPPED) == nullptr);
+	queue->start_profiling();
+	CHECK(queue->stop_profiling() < 1000000u);
+	std::printf("dropin_test: %s\n", failures ? "FAILED" : "ok");
+	return failures ? 1 : 0;
+}
