@@ -32,6 +32,50 @@ template <int BYTES> __device__ __forceinline__ void put_elem(uint32_t* w, int i
 }
 
 
+
+// ------------------------------------------------------------------------------------------------------
+// packed fp32 pairs: sm_100a issues two IEEE fp32 operations per instruction (FFMA2 / FADD2 / FMUL2, same
+// per-lane rounding as the scalar forms), which halves the issue slots of the float formats' arithmetic
+// ------------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(uint32_t lo, uint32_t hi) {
+	f32x2_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpk2(f32x2_t v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t splat2(float f) { return pk2(__float_as_uint(f), __float_as_uint(f)); }
+__device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c) {
+	f32x2_t r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+__device__ __forceinline__ f32x2_t add2_rn(f32x2_t a, f32x2_t b) {
+	f32x2_t r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2_t add2_rz(f32x2_t a, f32x2_t b) {
+	f32x2_t r;
+	asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b) {
+	f32x2_t r;
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2_t mul2_rn(f32x2_t a, f32x2_t b) {
+	f32x2_t r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2_t mul2_rz(f32x2_t a, f32x2_t b) {
+	f32x2_t r;
+	asm("mul.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // element codecs
 // ------------------------------------------------------------------------------------------------------
@@ -151,6 +195,68 @@ template <uint32_t EK> struct Codec {
 		}
 	}
 
+	// ---- the same codecs on pairs of elements (float formats only) -----------------------------------------
+	static __device__ __forceinline__ f32x2_t dec2_at(const uint32_t* w, int i0, int i1) {
+		if constexpr (EK == FLMIP_EK_UNORM8) {
+			const uint32_t m = magic_bits();
+			return fma2_rn(pk2(__byte_perm(w[i0 >> 2], m, 0x7440u | (uint32_t)(i0 & 3)), __byte_perm(w[i1 >> 2], m, 0x7440u | (uint32_t)(i1 & 3))),
+						   splat2(UNORM_C), splat2(-(MAGIC * UNORM_C)));
+		} else if constexpr (EK == FLMIP_EK_UNORM16) {
+			const uint32_t m = magic_bits();
+			return fma2_rn(pk2(__byte_perm(w[i0 >> 1], m, (i0 & 1) ? 0x7432u : 0x7410u), __byte_perm(w[i1 >> 1], m, (i1 & 1) ? 0x7432u : 0x7410u)),
+						   splat2(UNORM_C), splat2(-(MAGIC * UNORM_C)));
+		} else {
+			return pk2(dec_at(w, i0), dec_at(w, i1));
+		}
+	}
+	static __device__ __forceinline__ f32x2_t lerp_half2(f32x2_t a, f32x2_t b) {
+		static_assert(!IS_INT, "float formats only");
+		if constexpr (EK == FLMIP_EK_F32) return add2_rn(mul2_rn(sub2_rn(b, a), splat2(0.5f)), a);
+		else return fma2_rn(sub2_rn(b, a), splat2(0.5f), a);
+	}
+	// storage bits of two elements; bits above the storage width are unspecified
+	static __device__ __forceinline__ void enc2_dirty(f32x2_t v, uint32_t& lo, uint32_t& hi, uint32_t no_double) {
+		if constexpr (EK == FLMIP_EK_UNORM8) {
+			unpk2(add2_rz(mul2_rn(v, splat2(255.0f)), splat2(MAGIC)), lo, hi);
+		} else if constexpr (EK == FLMIP_EK_UNORM16) {
+			const f32x2_t t = no_double ? mul2_rn(v, splat2(65535.0f)) : mul2_rz(v, splat2(65535.0f));
+			unpk2(add2_rz(t, splat2(MAGIC)), lo, hi);
+		} else {
+			uint32_t a, b;
+			unpk2(v, a, b);
+			lo = enc_dirty(a, no_double);
+			hi = enc_dirty(b, no_double);
+		}
+	}
+	// encode NP pairs into packed words
+	template <int NP> static __device__ __forceinline__ void enc_pack2(const f32x2_t (&v)[NP], uint32_t* out, uint32_t no_double) {
+		if constexpr (BYTES == 4) {
+#pragma unroll
+			for (int p = 0; p < NP; ++p) enc2_dirty(v[p], out[2 * p], out[2 * p + 1], no_double);
+		} else if constexpr (BYTES == 2) {
+#pragma unroll
+			for (int p = 0; p < NP; ++p) {
+				uint32_t a, b;
+				if constexpr (EK == FLMIP_EK_F16) {
+					unpk2(v[p], a, b);
+					const __half2 h = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+					out[p] = *reinterpret_cast<const uint32_t*>(&h);
+				} else {
+					enc2_dirty(v[p], a, b, no_double);
+					out[p] = __byte_perm(a, b, 0x5410u);
+				}
+			}
+		} else {
+#pragma unroll
+			for (int p = 0; p < NP; p += 2) {
+				uint32_t a, b, c, d;
+				enc2_dirty(v[p], a, b, no_double);
+				enc2_dirty(v[p + 1], c, d, no_double);
+				out[p >> 1] = __byte_perm(__byte_perm(a, b, 0x0040u), __byte_perm(c, d, 0x0040u), 0x5410u);
+			}
+		}
+	}
+
 	// const_math.hpp:981-996 with t = 0.5 (power-of-two levels)
 	static __device__ __forceinline__ uint32_t lerp_half(uint32_t a, uint32_t b) {
 		if constexpr (!IS_INT) {
@@ -220,15 +326,29 @@ __device__ __forceinline__ void reduce_rows_2d(const uint32_t (&r0)[NW], const u
 	using C = Codec<EK>;
 	constexpr int NO = NW * 2 / C::BYTES; // output elements (= half the elements of one source row)
 	static_assert(NO >= CH && (NO % CH) == 0, "row must hold at least one x pair");
-	uint32_t v[NO];
+	if constexpr (!C::IS_INT) {
+		static_assert((NO % 2) == 0, "pairs of output elements");
+		f32x2_t v[NO / 2];
 #pragma unroll
-	for (int e = 0; e < NO; ++e) {
-		const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
-		const uint32_t x0 = C::lerp_half(C::dec_at(r0, ea), C::dec_at(r0, eb));
-		const uint32_t x1 = C::lerp_half(C::dec_at(r1, ea), C::dec_at(r1, eb));
-		v[e] = C::lerp_half(x0, x1);
+		for (int p = 0; p < NO / 2; ++p) {
+			const int e0 = 2 * p, e1 = 2 * p + 1;
+			const int ea0 = (2 * (e0 / CH)) * CH + (e0 % CH), eb0 = ea0 + CH, ea1 = (2 * (e1 / CH)) * CH + (e1 % CH), eb1 = ea1 + CH;
+			const f32x2_t x0 = C::lerp_half2(C::dec2_at(r0, ea0, ea1), C::dec2_at(r0, eb0, eb1));
+			const f32x2_t x1 = C::lerp_half2(C::dec2_at(r1, ea0, ea1), C::dec2_at(r1, eb0, eb1));
+			v[p] = C::lerp_half2(x0, x1);
+		}
+		C::template enc_pack2<NO / 2>(v, out, no_double);
+	} else {
+		uint32_t v[NO];
+#pragma unroll
+		for (int e = 0; e < NO; ++e) {
+			const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
+			const uint32_t x0 = C::lerp_half(C::dec_at(r0, ea), C::dec_at(r0, eb));
+			const uint32_t x1 = C::lerp_half(C::dec_at(r1, ea), C::dec_at(r1, eb));
+			v[e] = C::lerp_half(x0, x1);
+		}
+		C::template enc_pack<NO>(v, out, no_double);
 	}
-	C::template enc_pack<NO>(v, out, no_double);
 }
 
 // r[z][y]: rows (y, y+1) of slices (z, z+1)
@@ -238,17 +358,33 @@ __device__ __forceinline__ void reduce_rows_3d(const uint32_t (&r00)[NW], const 
 	using C = Codec<EK>;
 	constexpr int NO = NW * 2 / C::BYTES;
 	static_assert(NO >= CH && (NO % CH) == 0, "row must hold at least one x pair");
-	uint32_t v[NO];
+	if constexpr (!C::IS_INT) {
+		static_assert((NO % 2) == 0, "pairs of output elements");
+		f32x2_t v[NO / 2];
 #pragma unroll
-	for (int e = 0; e < NO; ++e) {
-		const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
-		const uint32_t x00 = C::lerp_half(C::dec_at(r00, ea), C::dec_at(r00, eb));
-		const uint32_t x01 = C::lerp_half(C::dec_at(r01, ea), C::dec_at(r01, eb));
-		const uint32_t x10 = C::lerp_half(C::dec_at(r10, ea), C::dec_at(r10, eb));
-		const uint32_t x11 = C::lerp_half(C::dec_at(r11, ea), C::dec_at(r11, eb));
-		v[e] = C::lerp_half(C::lerp_half(x00, x01), C::lerp_half(x10, x11));
+		for (int p = 0; p < NO / 2; ++p) {
+			const int e0 = 2 * p, e1 = 2 * p + 1;
+			const int ea0 = (2 * (e0 / CH)) * CH + (e0 % CH), eb0 = ea0 + CH, ea1 = (2 * (e1 / CH)) * CH + (e1 % CH), eb1 = ea1 + CH;
+			const f32x2_t x00 = C::lerp_half2(C::dec2_at(r00, ea0, ea1), C::dec2_at(r00, eb0, eb1));
+			const f32x2_t x01 = C::lerp_half2(C::dec2_at(r01, ea0, ea1), C::dec2_at(r01, eb0, eb1));
+			const f32x2_t x10 = C::lerp_half2(C::dec2_at(r10, ea0, ea1), C::dec2_at(r10, eb0, eb1));
+			const f32x2_t x11 = C::lerp_half2(C::dec2_at(r11, ea0, ea1), C::dec2_at(r11, eb0, eb1));
+			v[p] = C::lerp_half2(C::lerp_half2(x00, x01), C::lerp_half2(x10, x11));
+		}
+		C::template enc_pack2<NO / 2>(v, out, no_double);
+	} else {
+		uint32_t v[NO];
+#pragma unroll
+		for (int e = 0; e < NO; ++e) {
+			const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
+			const uint32_t x00 = C::lerp_half(C::dec_at(r00, ea), C::dec_at(r00, eb));
+			const uint32_t x01 = C::lerp_half(C::dec_at(r01, ea), C::dec_at(r01, eb));
+			const uint32_t x10 = C::lerp_half(C::dec_at(r10, ea), C::dec_at(r10, eb));
+			const uint32_t x11 = C::lerp_half(C::dec_at(r11, ea), C::dec_at(r11, eb));
+			v[e] = C::lerp_half(C::lerp_half(x00, x01), C::lerp_half(x10, x11));
+		}
+		C::template enc_pack<NO>(v, out, no_double);
 	}
-	C::template enc_pack<NO>(v, out, no_double);
 }
 
 // one destination texel from 4 / 8 individually addressed source texels (cascade levels)
@@ -999,6 +1135,10 @@ extern "C" __global__ void __launch_bounds__(256) flmip_fill(const __grid_consta
 #define FLMIP_FAST_KERNELS_FOR_KIND(K) \
 	FLMIP_FAST_KERNEL(2, K, 1) FLMIP_FAST_KERNEL(2, K, 2) FLMIP_FAST_KERNEL(2, K, 4) FLMIP_FAST_KERNEL(3, K, 1) FLMIP_FAST_KERNEL(3, K, 2) FLMIP_FAST_KERNEL(3, K, 4)
 
+// -DFLMIP_DEV_ONLY: a handful of instantiations for quick SASS inspection (never shipped)
+#ifdef FLMIP_DEV_ONLY
+FLMIP_FAST_KERNEL(2, 2, 4) FLMIP_FAST_KERNEL(2, 1, 4) FLMIP_FAST_KERNEL(3, 0, 1) FLMIP_FAST_KERNEL(2, 0, 4) FLMIP_FAST_KERNEL(2, 4, 4)
+#else
 FLMIP_FAST_KERNELS_FOR_KIND(0)
 FLMIP_FAST_KERNELS_FOR_KIND(1)
 FLMIP_FAST_KERNELS_FOR_KIND(2)
@@ -1011,3 +1151,4 @@ FLMIP_FAST_KERNELS_FOR_KIND(8)
 FLMIP_FAST_KERNELS_FOR_KIND(9)
 FLMIP_FAST_KERNELS_FOR_KIND(10)
 FLMIP_FAST_KERNELS_FOR_KIND(11)
+#endif
