@@ -5,7 +5,10 @@
 	.global flmip_cubin_begin
 	.type flmip_cubin_begin, @object
 flmip_cubin_begin:
-	.incbin "mip_kernels.cubin"
+#ifndef FLMIP_CUBIN_PATH
+#define FLMIP_CUBIN_PATH "mip_kernels.cubin"
+#endif
+	.incbin FLMIP_CUBIN_PATH
 	.global flmip_cubin_end
 	.type flmip_cubin_end, @object
 flmip_cubin_end:
