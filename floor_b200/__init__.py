@@ -31,6 +31,8 @@ EXPORTS = [
     "flmip_image_data_size", "flmip_image_get_level_info", "flmip_image_device_ptr", "flmip_image_plan",
     "flmip_image_upload", "flmip_image_download", "flmip_image_write", "flmip_image_zero",
     "flmip_mip_chain_generate", "flmip_mip_chain_generate_from", "flmip_image_fill_synthetic",
+    "flmip_image_blit", "flmip_image_create_tiled_twin", "flmip_tiled_destroy", "flmip_image_copy_to_tiled",
+    "flmip_image_copy_from_tiled", "flmip_tiled_download", "flmip_device_cu_context",
 ]
 
 
@@ -110,6 +112,13 @@ def lib() -> ctypes.CDLL:
         "flmip_mip_chain_generate": (i32, [vp, vp]),
         "flmip_mip_chain_generate_from": (i32, [vp, u32, vp]),
         "flmip_image_fill_synthetic": (i32, [vp, u64, u64, vp]),
+        "flmip_image_blit": (i32, [vp, vp, vp]),
+        "flmip_image_create_tiled_twin": (i32, [vp, ctypes.POINTER(vp)]),
+        "flmip_tiled_destroy": (i32, [i32, vp]),
+        "flmip_image_copy_to_tiled": (i32, [vp, vp, u32, u32, vp]),
+        "flmip_image_copy_from_tiled": (i32, [vp, vp, u32, u32, vp]),
+        "flmip_tiled_download": (i32, [vp, vp, vp, ctypes.c_size_t, u32, u32, vp]),
+        "flmip_device_cu_context": (i32, [i32, ctypes.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

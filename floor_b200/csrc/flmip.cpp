@@ -51,7 +51,8 @@ int fail(int code, const char* fmt, ...) {
 	F(cuCtxPopCurrent) F(cuMemAlloc) F(cuMemFree) F(cuMemsetD8Async) F(cuMemsetD32Async) F(cuMemcpyHtoDAsync) F(cuMemcpyDtoHAsync) \
 	F(cuMemcpy3DAsync) F(cuMemHostAlloc) F(cuMemFreeHost) F(cuStreamCreate) F(cuStreamDestroy) F(cuStreamSynchronize)            \
 	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
-	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuTensorMapEncodeTiled)
+	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
+	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy)
 
 struct driver_api {
 #define FL_DECL(name) decltype(&name) p_##name = nullptr;
@@ -762,6 +763,129 @@ int flmip_image_zero(flmip_image img, flmip_stream stream) {
 	WITH_DEVICE(img->device)
 	CU_TRY(cu.p_cuMemsetD8Async(img->mem, 0, img->total_size, (CUstream)stream), "cuMemsetD8Async");
 	return FLMIP_OK;
+}
+
+// -- blit / clone support: device_image::blit (device_image.hpp:96-101; CUDA inherits the `return false` stub, so
+//    clone(copy_contents = true) copies nothing there) -- on linear images it is one device-to-device copy.
+int flmip_image_blit(flmip_image dst, flmip_image src, flmip_stream stream) {
+	if (check_image(dst) || check_image(src)) return FLMIP_ERR_INVALID;
+	// blit_check (device_image.cpp:470-501): identical dim, layer count, size and format; no compressed formats
+	if (memcmp(dst->dim, src->dim, sizeof(dst->dim)) != 0) return fail(FLMIP_ERR_INVALID, "blit: dim mismatch");
+	if (dst->layers != src->layers) return fail(FLMIP_ERR_INVALID, "blit: layer count mismatch: src %u != dst %u", src->layers, dst->layers);
+	if ((dst->type & T_FORMAT_MASK) != (src->type & T_FORMAT_MASK) || dst->channels != src->channels)
+		return fail(FLMIP_ERR_INVALID, "blit: format mismatch");
+	if (dst->device != src->device) return fail(FLMIP_ERR_INVALID, "blit: images live on different devices");
+	// levels both images have (a clone may carry a different mip_level_limit)
+	const uint32_t levels = dst->level_count < src->level_count ? dst->level_count : src->level_count;
+	const uint64_t bytes = src->levels[levels - 1].offset + src->levels[levels - 1].size;
+	if (bytes == 0 || dst == src) return FLMIP_OK;
+	WITH_DEVICE(dst->device)
+	CU_TRY(cu.p_cuMemcpyDtoDAsync(dst->mem, src->mem, bytes, (CUstream)stream), "cuMemcpyDtoDAsync(blit)");
+	return FLMIP_OK;
+}
+
+int flmip_device_cu_context(int device, void** out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	device_state* ds = nullptr;
+	const int rc = get_device(device, &ds);
+	if (rc != FLMIP_OK) return rc;
+	*out = ds->ctx;
+	return FLMIP_OK;
+}
+
+// -- interop with floor's tiled CUDA images (CUmipmappedArray + texture / surface objects,
+//    src/device/cuda/cuda_image.cpp:158-539): a twin array with the reference's descriptor, and copies between the
+//    linear image and the array so that kernels which still sample through texture objects see the generated chain.
+int flmip_image_create_tiled_twin(flmip_image img, void** out_mipmapped_array) {
+	if (check_image(img) || !out_mipmapped_array) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out_mipmapped_array = nullptr;
+	if (img->dc < 2) return fail(FLMIP_ERR_UNSUPPORTED, "tiled interop covers 2D, 2D-array, cube, cube-array and 3D images");
+	// format LUT of cuda_image.cpp:197-207 (normalization is a property of the texture object, not of the array)
+	CUarray_format fmt;
+	switch (img->elem_kind) {
+		case FLMIP_EK_F32: fmt = CU_AD_FORMAT_FLOAT; break;
+		case FLMIP_EK_F16: fmt = CU_AD_FORMAT_HALF; break;
+		case FLMIP_EK_UNORM8: case FLMIP_EK_U8: fmt = CU_AD_FORMAT_UNSIGNED_INT8; break;
+		case FLMIP_EK_SNORM8: case FLMIP_EK_I8: fmt = CU_AD_FORMAT_SIGNED_INT8; break;
+		case FLMIP_EK_UNORM16: case FLMIP_EK_U16: fmt = CU_AD_FORMAT_UNSIGNED_INT16; break;
+		case FLMIP_EK_SNORM16: case FLMIP_EK_I16: fmt = CU_AD_FORMAT_SIGNED_INT16; break;
+		case FLMIP_EK_U32: fmt = CU_AD_FORMAT_UNSIGNED_INT32; break;
+		default: fmt = CU_AD_FORMAT_SIGNED_INT32; break;
+	}
+	const bool is_array = (img->type & T_FLAG_ARRAY) != 0, is_cube = (img->type & T_FLAG_CUBE) != 0;
+	CUDA_ARRAY3D_DESCRIPTOR desc;
+	memset(&desc, 0, sizeof(desc));
+	desc.Width = img->dim[0];
+	desc.Height = img->dim[1];
+	desc.Depth = img->dc == 3 ? img->dim[2] : ((is_array || is_cube) ? img->layers : 0u); // cuda_image.cpp:166-171
+	desc.Format = fmt;
+	desc.NumChannels = img->channels;
+	desc.Flags = (is_array ? CUDA_ARRAY3D_LAYERED : 0u) | (is_cube ? CUDA_ARRAY3D_CUBEMAP : 0u) | CUDA_ARRAY3D_SURFACE_LDST;
+	WITH_DEVICE(img->device)
+	CUmipmappedArray arr = nullptr;
+	CU_TRY(cu.p_cuMipmappedArrayCreate(&arr, &desc, img->level_count), "cuMipmappedArrayCreate");
+	*out_mipmapped_array = arr;
+	return FLMIP_OK;
+}
+
+int flmip_tiled_destroy(int device, void* mipmapped_array) {
+	if (!mipmapped_array) return FLMIP_OK;
+	WITH_DEVICE(device)
+	CU_TRY(cu.p_cuMipmappedArrayDestroy((CUmipmappedArray)mipmapped_array), "cuMipmappedArrayDestroy");
+	return FLMIP_OK;
+}
+
+} // extern "C"
+
+namespace {
+enum class tiled_dir { to_tiled, from_tiled, tiled_to_host };
+// one cuMemcpy3DAsync per level: rows x height x (depth | layers) between the level-major linear layout and the level's CUarray
+int tiled_copy(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, tiled_dir dir, void* host, size_t host_size,
+			   CUstream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (!mipmapped_array) return fail(FLMIP_ERR_INVALID, "null array");
+	if (img->dc < 2) return fail(FLMIP_ERR_UNSUPPORTED, "tiled interop covers 2D, 2D-array, cube, cube-array and 3D images");
+	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
+	const uint64_t begin = img->levels[level_first].offset, end = img->levels[level_last].offset + img->levels[level_last].size;
+	if (dir == tiled_dir::tiled_to_host && (!host || host_size < end - begin)) return fail(FLMIP_ERR_INVALID, "tiled download: insufficient host buffer");
+	WITH_DEVICE(img->device)
+	for (uint32_t level = level_first; level <= level_last; ++level) {
+		const flmip_level_info& li = img->levels[level];
+		if (li.size == 0) continue; // empty level (zero dim quirk); the array's level has max(1, dim >> level) texels, left untouched
+		CUarray arr = nullptr;
+		CU_TRY(cu.p_cuMipmappedArrayGetLevel(&arr, (CUmipmappedArray)mipmapped_array, level), "cuMipmappedArrayGetLevel");
+		CUDA_MEMCPY3D c;
+		memset(&c, 0, sizeof(c));
+		const uint64_t row = (uint64_t)li.dim[0] * img->bpp;
+		c.WidthInBytes = row;
+		c.Height = li.dim[1];
+		c.Depth = img->dc == 3 ? li.dim[2] : img->layers;
+		if (dir == tiled_dir::to_tiled) {
+			c.srcMemoryType = CU_MEMORYTYPE_DEVICE; c.srcDevice = img->mem + li.offset; c.srcPitch = row; c.srcHeight = li.dim[1];
+			c.dstMemoryType = CU_MEMORYTYPE_ARRAY; c.dstArray = arr;
+		} else {
+			c.srcMemoryType = CU_MEMORYTYPE_ARRAY; c.srcArray = arr;
+			c.dstPitch = row; c.dstHeight = li.dim[1];
+			if (dir == tiled_dir::from_tiled) { c.dstMemoryType = CU_MEMORYTYPE_DEVICE; c.dstDevice = img->mem + li.offset; }
+			else { c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = static_cast<uint8_t*>(host) + (li.offset - begin); }
+		}
+		CU_TRY(cu.p_cuMemcpy3DAsync(&c, stream), "cuMemcpy3DAsync(tiled interop)");
+	}
+	return FLMIP_OK;
+}
+} // namespace
+
+extern "C" {
+
+int flmip_image_copy_to_tiled(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	return tiled_copy(img, mipmapped_array, level_first, level_last, tiled_dir::to_tiled, nullptr, 0, (CUstream)stream);
+}
+int flmip_image_copy_from_tiled(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	return tiled_copy(img, mipmapped_array, level_first, level_last, tiled_dir::from_tiled, nullptr, 0, (CUstream)stream);
+}
+int flmip_tiled_download(flmip_image geometry, void* mipmapped_array, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last,
+						 flmip_stream stream) {
+	return tiled_copy(geometry, mipmapped_array, level_first, level_last, tiled_dir::tiled_to_host, dst, dst_size, (CUstream)stream);
 }
 
 int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream) {

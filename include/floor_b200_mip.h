@@ -103,6 +103,22 @@ int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t l
 int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
 					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream);
 int flmip_image_zero(flmip_image img, flmip_stream stream);          /* cuda_image::zero, cuda_image.cpp:675-701 */
+/* device_image::blit (device_image.hpp:96-101, checks of device_image.cpp:470-501): every level both images have, device to
+ * device.  The reference's CUDA image inherits the `return false` stub, so its clone(copy_contents) copies nothing. */
+int flmip_image_blit(flmip_image dst, flmip_image src, flmip_stream stream);
+
+/* -- interop with floor's tiled CUDA images (CUmipmappedArray sampled through texture / surface objects,
+ *    cuda_image.cpp:158-539): create an array with the reference's descriptor for this image, copy whole levels between
+ *    the linear image and the array (one cuMemcpy3DAsync per level), read an array back to the host in floor's layout.
+ *    `mipmapped_array` is a CUmipmappedArray; arrays created by the original cuda_image can be passed as they are. */
+int flmip_image_create_tiled_twin(flmip_image img, void** out_mipmapped_array);
+int flmip_tiled_destroy(int device, void* mipmapped_array);
+int flmip_image_copy_to_tiled(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, flmip_stream stream);
+int flmip_image_copy_from_tiled(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, flmip_stream stream);
+int flmip_tiled_download(flmip_image geometry, void* mipmapped_array, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last,
+						 flmip_stream stream);
+/* the CUcontext the library uses on `device` (cuda_device::ctx, include/floor/device/cuda/cuda_device.hpp:30-86) */
+int flmip_device_cu_context(int device, void** out);
 
 /* -- THE hot path: device_image::generate_mip_map_chain (src/device/device_image.cpp:235-328) + the
  *    libfloor_mip_map_minify_* kernels (include/floor/device/backend/mip_map_minify.hpp:89-126).
