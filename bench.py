@@ -279,35 +279,50 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_cpu(workload: str, steps: int, warmup: int):
-    """times the restated Host-Compute path (oracle/, kind "port": the reference itself needs clang >= 19 and cannot be
-    built in this image) on the box's host cores.  One step = the full chain of the workload image (per-layer sample for
-    the layered configs)."""
+    """times the reference's CPU implementation of the path on the box's host cores.  kind "reference": oracle/_ref, the
+    reference's own Host-Compute minify kernels + software sampler compiled from /root/reference by oracle/build_ref.py (the
+    .so travels with the repo); kind "port": the C restatement (oracle/minify_oracle.c) when oracle/_ref is absent.
+    One step = the full chain of the workload image (a few layers / one cube for the layered configs: the reference's
+    32-bit level offsets cannot address more, and layers are independent)."""
     import oracle
+    from oracle import ref
+    use_ref = ref.available()
     desc, dim, t, sharded, cid = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     sample = "full workload image"
     sdim = list(dim)
     if sharded:
-        sdim[2] = 8 if workload == "c3" else 1  # a few layers / one cube: the oracle runs per layer anyway
+        sdim[2] = 8 if workload == "c3" else 1
         sample = f"{sdim[2]} of {dim[2]} {'cubes' if t & T.FLAG_CUBE else 'layers'} (layers are independent)"
+    elif workload == "n2":
+        sdim[2] = 8
+        sample = f"8 of {dim[2]} layers (layers are independent)"
     sdim = tuple(sdim)
     l0 = oracle.fill_synthetic(sdim, t, cid)
     total = oracle.image_data_size(sdim, t)
-    buf = np.zeros(total, dtype=np.uint8)
+    buf = np.zeros(total + 64, dtype=np.uint8)
     buf[: l0.size] = l0
+    if use_ref:
+        run = lambda: ref.generate_in_place(buf, sdim, t, threads=cores, fast=True)
+        what = ("reference Host-Compute kernels (mip_map_minify.hpp + host_image.hpp compiled by g++ with the reference's release "
+                "flags minus -ffast-math: -O3 -funroll-loops -march=corei7-avx -mf16c; one thread pool per launch, without libfloor's "
+                "per-texel fibers)")
+    else:
+        run = lambda: oracle.generate_in_place(buf, sdim, t, threads=cores)
+        what = "Host-Compute restatement (optimistic: omits libfloor's per-launch thread spawn and per-texel fibers)"
     for _ in range(warmup):
-        oracle.generate_in_place(buf, sdim, t, threads=cores)
+        run()
     if steps is None:
         # bounded sample: about 10 s of CPU work, at most 64 chains
         t0 = time.perf_counter()
-        oracle.generate_in_place(buf, sdim, t, threads=cores)
+        run()
         steps = int(min(64, max(1, round(10.0 / max(time.perf_counter() - t0, 1e-4)))))
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle.generate_in_place(buf, sdim, t, threads=cores)
+        run()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": round(total / dt / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": sample + f"; {steps} step(s) of {dt:.3f} s; Host-Compute restatement (optimistic: omits libfloor's per-launch thread spawn and per-texel fibers)",
+    return {"value": round(total / dt / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": sample + f"; {steps} step(s) of {dt:.3f} s; {what}",
             "seconds_per_step": round(dt, 4), "bytes_per_step": int(total)}
 
 
@@ -319,7 +334,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "mip_chain_throughput", "value": base["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
            "warmup": min(args.warmup, 1), "ms_per_step": round(base["seconds_per_step"] * 1e3, 3), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
-           "config": {"workload": desc, "note": "CPU arm: Host-Compute restatement on the host cores (the reference needs clang >= 19 + libc++ + SDL3 and does not build here)"},
+           "config": {"workload": desc, "note": "CPU arm on the host cores: " + ("the reference's own Host-Compute kernels (oracle/_ref)" if base["kind"] == "reference" else "Host-Compute restatement (oracle/_ref absent)")},
            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

@@ -1,8 +1,12 @@
 """ctypes front end of the CPU oracle (oracle/minify_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
-``--impl reference`` legs of bench.py -- never by the floor_b200 package.  Parity is "unpinned":
-the reference has no golden vectors for this path and does not compile here.
+``--impl reference`` legs of bench.py -- never by the floor_b200 package.
+
+Pinned against the reference itself: the reference ships no golden vectors for this path, but its Host-Compute minify
+kernels, software sampler and image-size helpers compile with g++ through oracle/build_ref.py (-> oracle/_ref, front end
+oracle/ref.py); tests/test_reference_pin.py requires this restatement to match them bit for bit, and
+tests/golden/golden_ref.json freezes reference-computed chains ("Oracle").
 """
 from __future__ import annotations
 

@@ -2,10 +2,15 @@
  * minify_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
  *
  * CPU restatement of libfloor's Host-Compute mip-map minification path, used as the parity
- * oracle and as the "port" CPU baseline of bench.py.  PARITY UNPINNED: the reference ships no
- * tests / golden vectors for this path and cannot be compiled in this image (clang >= 19 only;
- * see DESIGN.md), so this file is pinned by source semantics alone, evaluated in strict IEEE-754
- * order (build with -fno-fast-math -ffp-contract=off).
+ * oracle and as the "port" CPU baseline of bench.py.  PINNED AGAINST THE REFERENCE ITSELF: the
+ * reference ships no tests / golden vectors for this path and libfloor as a whole needs
+ * clang >= 19, but its Host-Compute minify kernels + software sampler + image-size helpers do
+ * compile with g++ through oracle/build_ref.py (-> oracle/_ref/); tests/test_reference_pin.py
+ * requires this restatement to equal them bit for bit (all formats, 2D / array / cube / 3D,
+ * POT and NPOT, both encoder-scale modes, adversarial floats, BASELINE configs), and
+ * tests/golden/golden_ref.json freezes reference-computed chains.  1D and depth images are the
+ * exception (their reference kernels do not compile with g++): pinned by source semantics and
+ * the numpy emulation only.  Evaluated in strict IEEE-754 order (-fno-fast-math -ffp-contract=off).
  *
  * Each function cites the reference file:line (relative to a2flo/floor) it follows:
  *   kernel ................. include/floor/device/backend/mip_map_minify.hpp:78-108
