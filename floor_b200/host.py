@@ -147,6 +147,7 @@ class device_image:
                  force_generic: bool = False, units: bool | None = None):
         from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, LevelInfo
         self.dev = cqueue.dev
+        self._create_kw = {"no_double": no_double, "force_generic": force_generic, "units": units}
         dim = list(image_dim) + [0] * (4 - len(image_dim))
         # device_image::handle_image_type (device_image.hpp:70-91)
         if flags & MEMORY_FLAG.GENERATE_MIP_MAPS:
@@ -263,6 +264,68 @@ class device_image:
                 self.generate_mip_map_chain(cqueue)
         del self._mappings[mapped.ctypes.data]
         return True
+
+    def blit(self, cqueue: device_queue, src: "device_image") -> bool:
+        """device_image::blit (device_image.hpp:96-101) with the checks of blit_check (device_image.cpp:470-501); blocking.
+        The reference's CUDA image inherits the `return false` stub; on linear images it is one device-to-device copy."""
+        from . import FlmipError
+        if src.image_data_size != self.image_data_size:
+            return False  # "blit: size mismatch"
+        try:
+            _check(_L().flmip_image_blit(self._handle, src._handle, cqueue._stream))
+        except FlmipError:
+            return False
+        cqueue.finish()
+        return True
+
+    def blit_async(self, cqueue: device_queue, src: "device_image") -> bool:
+        from . import FlmipError
+        try:
+            _check(_L().flmip_image_blit(self._handle, src._handle, cqueue._stream))
+        except FlmipError:
+            return False
+        return True
+
+    def clone(self, cqueue: device_queue, copy_contents: bool = False, flags_override: int = 0, image_type_override: int = 0) -> "device_image":
+        """device_image::clone (device_image.cpp:446-466): same dim, type (unless overridden), flags and level count; host data
+        is never copied into the clone; `copy_contents` blits"""
+        flags = (flags_override if flags_override else self.flags) | MEMORY_FLAG.NO_INITIAL_COPY
+        t = image_type_override if image_type_override else (self.image_type | (IMAGE_TYPE.FLAG_MIPMAPPED if self.mip_level_count > 1 else 0))
+        ret = device_image(cqueue, self.image_dim, t, None, flags, self.mip_level_count, **self._create_kw)
+        if copy_contents:
+            ret.blit(cqueue, self)
+        return ret
+
+    # ---- interop with floor's tiled CUDA images (CUmipmappedArray, cuda_image.cpp:158-539) ----
+    def create_tiled_twin(self) -> ctypes.c_void_p:
+        """a CUmipmappedArray with the descriptor the reference's cuda_image would create for this image"""
+        arr = ctypes.c_void_p()
+        _check(_L().flmip_image_create_tiled_twin(self._handle, ctypes.byref(arr)))
+        return arr
+
+    def destroy_tiled(self, arr) -> None:
+        _check(_L().flmip_tiled_destroy(self.dev.index, arr))
+
+    def copy_to_tiled(self, cqueue: device_queue, arr, level_first: int = 0, level_last: int | None = None, sync: bool = True):
+        last = self.mip_level_count - 1 if level_last is None else level_last
+        _check(_L().flmip_image_copy_to_tiled(self._handle, arr, level_first, last, cqueue._stream))
+        if sync:
+            cqueue.finish()
+
+    def copy_from_tiled(self, cqueue: device_queue, arr, level_first: int = 0, level_last: int | None = None, sync: bool = True):
+        last = self.mip_level_count - 1 if level_last is None else level_last
+        _check(_L().flmip_image_copy_from_tiled(self._handle, arr, level_first, last, cqueue._stream))
+        if sync:
+            cqueue.finish()
+
+    def tiled_download(self, cqueue: device_queue, arr, level_first: int = 0, level_last: int | None = None) -> np.ndarray:
+        """reads a CUmipmappedArray of this image's geometry back in floor's host layout"""
+        last = self.mip_level_count - 1 if level_last is None else level_last
+        n = self.levels[last]["offset"] + self.levels[last]["size"] - self.levels[level_first]["offset"]
+        out = np.empty(n, dtype=np.uint8)
+        _check(_L().flmip_tiled_download(self._handle, arr, out.ctypes.data, n, level_first, last, cqueue._stream))
+        cqueue.finish()
+        return out
 
     # ---- helpers beyond the reference API (tests / bench) ----
     def upload_levels(self, cqueue: device_queue, src, level_first: int = 0, level_last: int = 0, sync: bool = True, nbytes: int | None = None):

@@ -261,6 +261,85 @@ public:
 		cqueue.finish();
 		return true;
 	}
+	//! device_image::blit (device_image.hpp:96-101) with the checks of blit_check (device_image.cpp:470-501); blocking.
+	//! The reference's CUDA image inherits the `return false` stub (only Vulkan / Metal implement it); on linear images
+	//! it is one device-to-device copy of every level both images have.
+	virtual bool blit(const device_queue& cqueue, device_image& src) {
+		if (!blit_async(cqueue, src)) return false;
+		cqueue.finish();
+		return true;
+	}
+	virtual bool blit_async(const device_queue& cqueue, device_image& src) {
+		if (!handle || !src.handle) return false;
+		if (src.get_image_data_size() != image_data_size) {
+			FLB_LOG_ERROR("blit: size mismatch: src %zu != dst %zu", src.get_image_data_size(), image_data_size);
+			return false;
+		}
+		if (flmip_image_blit(handle, src.handle, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) {
+			FLB_LOG_ERROR("%s", flmip_last_error_string());
+			return false;
+		}
+		return true;
+	}
+	//! device_image::clone (device_image.cpp:446-466): same dim, type (unless overridden), flags and level count; host data is
+	//! never copied into the clone; `copy_contents` blits (which actually copies here)
+	std::shared_ptr<device_image> clone(const device_queue& cqueue, bool copy_contents = false, MEMORY_FLAG flags_override = MEMORY_FLAG::NONE,
+										IMAGE_TYPE image_type_override = IMAGE_TYPE::NONE, const char* clone_debug_label = nullptr) const {
+		auto clone_flags = (flags_override != MEMORY_FLAG::NONE ? flags_override : flags);
+		if (host_data.data() != nullptr) clone_flags |= MEMORY_FLAG::NO_INITIAL_COPY;
+		std::shared_ptr<device_image> ret;
+		try {
+			ret = std::make_shared<device_image>(cqueue, image_dim, image_type_override == IMAGE_TYPE::NONE ? image_type : image_type_override, host_data,
+												 clone_flags, mip_level_count, clone_debug_label);
+		} catch (const std::exception& e) {
+			FLB_LOG_ERROR("clone: %s", e.what());
+			return {};
+		}
+		if (!ret->is_valid()) return {};
+		if (copy_contents) ret->blit(cqueue, const_cast<device_image&>(*this));
+		return ret;
+	}
+
+	// ---- interop with floor's tiled CUDA images (CUmipmappedArray + texture / surface objects, cuda_image.cpp:158-539) ----
+	//! creates a CUmipmappedArray with the descriptor the original cuda_image uses for this image (caller destroys it)
+	void* create_tiled_twin() const {
+		void* arr = nullptr;
+		if (!handle || flmip_image_create_tiled_twin(handle, &arr) != FLMIP_OK) {
+			FLB_LOG_ERROR("%s", flmip_last_error_string());
+			return nullptr;
+		}
+		return arr;
+	}
+	void destroy_tiled(void* mipmapped_array) const { flmip_tiled_destroy(dev.device_id, mipmapped_array); }
+	//! linear -> CUmipmappedArray, levels [first, last]: publishes generated levels to kernels that sample through texture objects
+	bool copy_to_tiled(const device_queue& cqueue, void* mipmapped_array, uint32_t first_level, uint32_t last_level) const {
+		if (!handle || flmip_image_copy_to_tiled(handle, mipmapped_array, first_level, last_level, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) return false;
+		cqueue.finish();
+		return true;
+	}
+	//! CUmipmappedArray -> linear, levels [first, last]: pulls level 0 of an image the original cuda_image owns
+	bool copy_from_tiled(const device_queue& cqueue, void* mipmapped_array, uint32_t first_level, uint32_t last_level) {
+		if (!handle || flmip_image_copy_from_tiled(handle, mipmapped_array, first_level, last_level, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) return false;
+		cqueue.finish();
+		return true;
+	}
+	//! generate_mip_map_chain for an image that lives in a CUmipmappedArray (the original cuda_image's storage): level 0 in,
+	//! single-pass chain, generated levels out -- three stream-ordered steps, one host wait
+	bool generate_mip_map_chain_for_tiled(const device_queue& cqueue, void* mipmapped_array) {
+		void* stream = const_cast<void*>(cqueue.get_queue_ptr());
+		if (!handle || flmip_image_copy_from_tiled(handle, mipmapped_array, 0, 0, stream) != FLMIP_OK) return false;
+		if (flmip_mip_chain_generate(handle, stream) != FLMIP_OK) return false;
+		if (mip_level_count > 1 && flmip_image_copy_to_tiled(handle, mipmapped_array, 1, mip_level_count - 1, stream) != FLMIP_OK) return false;
+		cqueue.finish();
+		return true;
+	}
+	//! reads a CUmipmappedArray of this image's geometry back in floor's host layout
+	bool read_tiled_levels(const device_queue& cqueue, void* mipmapped_array, void* dst, size_t dst_size, uint32_t first_level, uint32_t last_level) const {
+		if (!handle || flmip_tiled_download(handle, mipmapped_array, dst, dst_size, first_level, last_level, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) return false;
+		cqueue.finish();
+		return true;
+	}
+
 	//! reads back whole levels [first, last] in host layout (what a harness needs to look at generated levels; the
 	//! reference can only do this through map() on an image created without GENERATE_MIP_MAPS)
 	bool read_levels(const device_queue& cqueue, void* dst, size_t dst_size, uint32_t first_level, uint32_t last_level) const {

@@ -122,6 +122,33 @@ int main(int argc, char** argv) {
 		CHECK(img->read_levels(*queue, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
 		CHECK(got == want);
 		CHECK(!img->write(*queue, l0.data(), l0.size(), { 1, 0, 0 }, extent, { 0, 0 }, { 0, 0 }));
+
+		// clone(copy_contents) really copies (the reference's CUDA blit is a `return false` stub), blit refuses a mismatch
+		auto twin = img->clone(*queue, true);
+		CHECK(twin != nullptr && twin->get_device_ptr() != img->get_device_ptr());
+		if (twin) {
+			std::fill(got.begin(), got.end(), uint8_t(0));
+			CHECK(twin->read_levels(*queue, got.data(), got.size(), 0, twin->get_mip_level_count() - 1));
+			CHECK(got == want);
+		}
+		auto small = ctx.create_image(*queue, { 64, 64, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA8 | IMAGE_TYPE::FLAG_MIPMAPPED);
+		CHECK(small != nullptr && !small->blit(*queue, *img));
+
+		// an image that lives in floor's tiled storage (CUmipmappedArray): level 0 in, chain, generated levels out
+		if (image_dim_count(type) >= 2) {
+			void* arr = img->create_tiled_twin();
+			CHECK(arr != nullptr);
+			if (arr) {
+				CHECK(img->copy_to_tiled(*queue, arr, 0, 0));
+				auto scratch = img->clone(*queue, false, MEMORY_FLAG::READ_WRITE | MEMORY_FLAG::HOST_READ_WRITE);
+				CHECK(scratch != nullptr && scratch->zero(*queue));
+				CHECK(scratch && scratch->generate_mip_map_chain_for_tiled(*queue, arr));
+				std::fill(got.begin(), got.end(), uint8_t(0));
+				CHECK(img->read_tiled_levels(*queue, arr, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
+				CHECK(got == want);
+				img->destroy_tiled(arr);
+			}
+		}
 	}
 	// constructor invariants throw (device_image.hpp:502-539); unsupported formats return nullptr (cuda_image.cpp:173-180)
 	bool threw = false;

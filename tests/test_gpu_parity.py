@@ -333,3 +333,62 @@ def test_cuda_path_against_reference_library(gpu_ctx, oracle_mod):
             want = ref.generate_mip_map_chain(l0, dim, t, threads=8)
             got, _ = gpu_chain(gpu_ctx, l0, dim, t)
             assert_same(got, want, t, dim, "vs reference library")
+
+
+def test_blit_and_clone(gpu_ctx, oracle_mod):
+    """device_image::blit / clone (device_image.cpp:446-501) on linear images: every level both images have is copied on the
+    device; mismatching dims / formats are refused like blit_check does"""
+    ctx, dev, q = gpu_ctx
+    dim, t = (256, 128, 3), T.IMAGE_2D_ARRAY | T.RGBA16F | M
+    l0 = oracle_mod.fill_synthetic(dim, t, 41)
+    want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4)
+    src = ctx.create_image(q, dim, t)
+    src.upload_levels(q, l0, 0, 0)
+    src.generate_mip_map_chain(q)
+    c = src.clone(q, copy_contents=True)
+    assert c.get_image_dim() == src.get_image_dim() and c.get_mip_level_count() == src.get_mip_level_count()
+    assert c.device_ptr() != src.device_ptr()
+    assert_same(c.download_levels(q), want, t, dim, "clone(copy_contents)")
+    e = src.clone(q, copy_contents=False)
+    e.zero(q)
+    assert not e.download_levels(q).any()
+    assert e.blit(q, src)
+    assert_same(e.download_levels(q), want, t, dim, "blit")
+    # a blitted level 0 regenerates to the same chain
+    e.zero(q)
+    other = ctx.create_image(q, (256, 128, 2), t)
+    assert not other.blit(q, src)  # layer count mismatch
+    other.destroy()
+    other = ctx.create_image(q, dim, T.IMAGE_2D_ARRAY | T.RGBA16 | M)
+    assert other.blit(q, src)  # same FORMAT_16 x 4 channels: blit_check only compares the format bits
+    other.destroy()
+    other = ctx.create_image(q, dim, T.IMAGE_2D_ARRAY | T.RGBA8 | M)
+    assert not other.blit(q, src)
+    for i in (src, c, e, other):
+        i.destroy()
+
+
+@pytest.mark.parametrize("base,dim,fmt", [(T.IMAGE_2D, (512, 256), T.RGBA8), (T.IMAGE_2D, (300, 200), T.RGBA16F), (T.IMAGE_2D_ARRAY, (128, 128, 5), T.RG16),
+                                          (T.IMAGE_CUBE, (64, 64), T.RGBA32F), (T.IMAGE_CUBE_ARRAY, (32, 32, 2), T.R32F), (T.IMAGE_3D, (64, 32, 16), T.R32F),
+                                          (T.IMAGE_3D, (20, 12, 10), T.RGBA8UI), (T.IMAGE_2D, (1024, 64), T.R16F)])
+def test_tiled_interop_round_trip(gpu_ctx, oracle_mod, base, dim, fmt):
+    """linear image -> CUmipmappedArray with the reference's descriptor (cuda_image.cpp:158-539) -> host, and back: the chain the
+    new kernel generated arrives in floor's tiled image bit for bit, level by level, and a tiled image's level 0 can be
+    pulled into a linear image to have its chain generated"""
+    ctx, dev, q = gpu_ctx
+    t = base | fmt | M
+    l0 = oracle_mod.fill_synthetic(dim, t, 43)
+    want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4)
+    img = ctx.create_image(q, dim, t)
+    img.upload_levels(q, l0, 0, 0)
+    arr = img.create_tiled_twin()
+    img.copy_to_tiled(q, arr, 0, 0)          # the "original cuda_image" holds level 0 only
+    img.zero(q)
+    img.copy_from_tiled(q, arr, 0, 0)        # pull level 0 in, generate, push the generated levels back
+    img.generate_mip_map_chain(q)
+    if img.get_mip_level_count() > 1:
+        img.copy_to_tiled(q, arr, 1, img.get_mip_level_count() - 1)
+    got = img.tiled_download(q, arr)
+    assert_same(got, want, t, dim, "tiled array contents")
+    img.destroy_tiled(arr)
+    img.destroy()
