@@ -140,7 +140,7 @@ int main(int argc, char** argv) {
 			CHECK(arr != nullptr);
 			if (arr) {
 				CHECK(img->copy_to_tiled(*queue, arr, 0, 0));
-				auto scratch = img->clone(*queue, false, MEMORY_FLAG::READ_WRITE | MEMORY_FLAG::HOST_READ_WRITE);
+				auto scratch = img->clone(*queue, false);
 				CHECK(scratch != nullptr && scratch->zero(*queue));
 				CHECK(scratch && scratch->generate_mip_map_chain_for_tiled(*queue, arr));
 				std::fill(got.begin(), got.end(), uint8_t(0));
