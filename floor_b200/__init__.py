@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 FLMIP_OK = 0
 ERR_NO_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_DRIVER, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
-IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER = 1, 2, 4, 8
+IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED = 1, 2, 4, 8, 16
 
 # every symbol include/floor_b200_mip.h declares (checked by tests/test_cabi.py without a GPU)
 EXPORTS = [

@@ -264,6 +264,9 @@ struct flmip_image_s {
 	uint32_t fast_smem = 0, fast_grid = 0; // dynamic shared memory and persistent grid of the single-pass launch
 	alignas(64) CUtensorMap tmap {};
 	std::string fast_name;
+	// levels the single-pass launch does not produce: multi-level tile kernel (2D / 3D) or one generic launch per level
+	bool tiled = false;
+	std::string tile_name;
 };
 
 namespace {
@@ -479,6 +482,91 @@ int launch_generic_level(flmip_image_s& im, device_state* ds, uint32_t level, CU
 	return launch(fn, (G.total + 255u) / 256u, 256, 0, stream, args);
 }
 
+// first level without texels (zero dim quirk, image_types.hpp:751-766): every later level is empty as well
+uint32_t populated_levels(const flmip_image_s& im) {
+	uint32_t n = 0;
+	while (n < im.level_count && im.levels[n].size != 0) ++n;
+	return n;
+}
+
+// The reference's sampler quirk the tile kernel has to honour (see axis_fetch in mip_kernels.cu): for destination texel 0
+// of a source level of N texels with fl(fl(1/N) * N) == pred(1.0f), the neighbour texel is 2, not 1.  Same IEEE fp32
+// operations as the device code (host_image.hpp:141-174, 869-894 with g = 0).
+bool axis_reads_texel_2(uint32_t n) {
+	if (n < 3) return false;
+	const float fn = (float)n;
+	volatile float coord = 1.0f * (1.0f / fn);
+	volatile float scaled = coord * fn;
+	const float frac = scaled - floorf(scaled);
+	volatile float ma = scaled + (frac < 0.5f ? -1.0f : 1.0f);
+	return ma >= 2.0f;
+}
+
+// levels one tile-kernel launch can produce from source level s: up to 6 (2D) / 4 (3D), cut before a level whose
+// texel-2 fetch would leave the 2-texel-wide remainder of a tile (produced level k reads level k - 1 of the tile,
+// which is tile >> (k - 1) texels wide)
+uint32_t tile_levels_from(const flmip_image_s& im, uint32_t s, uint32_t pop) {
+	const uint32_t tile[3] = { im.dc == 3 ? FLMIP_TILE3D_X : FLMIP_TILE2D_X, im.dc == 3 ? FLMIP_TILE3D_Y : FLMIP_TILE2D_Y, FLMIP_TILE3D_Z };
+	const uint32_t step = im.dc == 3 ? FLMIP_TILE3D_MAX_LEVELS : FLMIP_TILE_MAX_LEVELS;
+	uint32_t n = pop - 1u - s < step ? pop - 1u - s : step;
+	for (uint32_t k = 2; k <= n; ++k) {
+		for (uint32_t d = 0; d < im.dc; ++d) {
+			if ((tile[d] >> (k - 1u)) < 3u && axis_reads_texel_2(im.levels[s + k - 1u].dim[d])) return k - 1u;
+		}
+	}
+	return n;
+}
+
+// number of tile-kernel launches that produce levels (src_level, populated)
+uint32_t tile_launch_count(const flmip_image_s& im, uint32_t src_level) {
+	const uint32_t pop = populated_levels(im);
+	uint32_t n = 0;
+	for (uint32_t s = src_level; s + 1 < pop; s += tile_levels_from(im, s, pop)) ++n;
+	return n;
+}
+
+// multi-level tile kernel: levels src_level + 1 ... (stream-ordered launches of up to 6 (2D) / 4 (3D) levels each)
+int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, CUstream stream) {
+	const uint32_t pop = populated_levels(im);
+	CUfunction fn = nullptr;
+	uint32_t step = 0;
+	for (uint32_t s = src_level; s + 1 < pop; s += step) {
+		step = tile_levels_from(im, s, pop);
+		if (!fn) {
+			const int rc = get_function(ds, im.tile_name, 0, &fn);
+			if (rc != FLMIP_OK) return rc;
+		}
+		flmip_tile_params T;
+		memset(&T, 0, sizeof(T));
+		T.base = im.mem;
+		T.nlev = step;
+		for (uint32_t k = 0; k <= T.nlev; ++k) {
+			const flmip_level_info& li = im.levels[s + k];
+			T.level_off[k] = li.offset;
+			T.slice[k] = li.slice_size;
+			T.dim[k][0] = li.dim[0]; T.dim[k][1] = li.dim[1]; T.dim[k][2] = im.dc == 3 ? li.dim[2] : 1u;
+			if (k < T.nlev) {
+				for (uint32_t d = 0; d < im.dc; ++d) {
+					// device_image.cpp:311-312 and host_image.cpp:96-107, evaluated in IEEE fp32 on the host
+					T.inv_prev[k][d] = 1.0f / (float)li.dim[d];
+					T.fdim[k][d] = (float)li.dim[d];
+					T.fdim_excl[k][d] = nextafterf((float)li.dim[d], 0.0f);
+				}
+			}
+		}
+		const uint32_t tx = im.dc == 3 ? FLMIP_TILE3D_X : FLMIP_TILE2D_X, ty = im.dc == 3 ? FLMIP_TILE3D_Y : FLMIP_TILE2D_Y;
+		T.tiles[0] = (T.dim[0][0] + tx - 1u) / tx;
+		T.tiles[1] = (T.dim[0][1] + ty - 1u) / ty;
+		T.tiles[2] = im.dc == 3 ? (T.dim[0][2] + FLMIP_TILE3D_Z - 1u) / FLMIP_TILE3D_Z : 1u;
+		T.layers = im.layers;
+		T.no_double = im.no_double;
+		void* args[] = { &T };
+		const int rc = launch(fn, (uint64_t)T.tiles[0] * T.tiles[1] * T.tiles[2] * im.layers, 256, 0, stream, args);
+		if (rc != FLMIP_OK) return rc;
+	}
+	return FLMIP_OK;
+}
+
 int check_image(flmip_image img) {
 	if (!img) return fail(FLMIP_ERR_INVALID, "null image handle");
 	return FLMIP_OK;
@@ -620,7 +708,17 @@ int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim
 	if (rc != FLMIP_OK) { delete im; return rc; }
 	CUresult r = cu.p_cuMemAlloc(&im->mem, im->total_size);
 	if (r != CUDA_SUCCESS) { delete im; return cu_fail(r, "cuMemAlloc(image)"); }
-	rc = plan_fast(*im, ds, flags);
+	rc = plan_fast(*im, ds, (flags & FLMIP_IMAGE_FORCE_TILED) ? (flags | FLMIP_IMAGE_FORCE_GENERIC) : flags);
+	if (rc == FLMIP_OK && im->dc >= 2 && ((flags & FLMIP_IMAGE_FORCE_TILED) || !(flags & FLMIP_IMAGE_FORCE_GENERIC))) {
+		char name[64];
+		snprintf(name, sizeof(name), "flmip_tile%ud_k%u_c%u", im->dc, im->elem_kind, im->channels);
+		im->tile_name = name;
+		im->tiled = true;
+		if (im->level_count > 1) {
+			CUfunction fn = nullptr;
+			rc = get_function(ds, im->tile_name, 0, &fn); // resolve now: fail at creation, not at first use
+		}
+	}
 	if (rc != FLMIP_OK) {
 		if (im->counters) cu.p_cuMemFree(im->counters);
 		cu.p_cuMemFree(im->mem);
@@ -671,9 +769,13 @@ int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast
 	uint32_t n = 0;
 	const uint32_t first_generic = img->fast ? img->fast_level_count : 1u;
 	if (img->fast) ++n;
-	for (uint32_t l = first_generic; l < img->level_count; ++l) {
-		const flmip_level_info& li = img->levels[l];
-		if (li.size != 0) ++n;
+	if (img->tiled) {
+		n += tile_launch_count(*img, first_generic - 1u);
+	} else {
+		for (uint32_t l = first_generic; l < img->level_count; ++l) {
+			const flmip_level_info& li = img->levels[l];
+			if (li.size != 0) ++n;
+		}
 	}
 	if (uses_single_pass) *uses_single_pass = img->fast ? 1u : 0u;
 	if (fast_levels) *fast_levels = img->fast ? img->fast_level_count : 0u;
@@ -903,7 +1005,9 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 		if (rc != FLMIP_OK) return rc;
 		next = img->fast_level_count;
 	}
-	// general path: one launch per remaining level, stream-ordered (the reference syncs the host after each: device_image.cpp:322)
+	// remaining levels: the multi-level tile kernel (2D / 3D, any size) ...
+	if (img->tiled) return launch_tile_levels(*img, ds, next - 1u, (CUstream)stream);
+	// ... or the literal general path: one launch per level, stream-ordered (the reference syncs the host after each: device_image.cpp:322)
 	for (uint32_t level = next; level < img->level_count; ++level) {
 		const int rc = launch_generic_level(*img, ds, level, (CUstream)stream);
 		if (rc != FLMIP_OK) return rc;

@@ -1070,6 +1070,208 @@ __device__ __forceinline__ void generic_texel(const flmip_generic_params& P, uin
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// multi-level tile kernel (flmip_tile2d_* / flmip_tile3d_*): any image size.
+//
+// For NPOT levels the sample point (2g+1) * fl(1/N) * N is 2g+1 +- a few ulp, so along each axis the reference's
+// sampler (host_image.hpp:141-174, 869-929) reads the "active" texel B (the one the point falls into: 2g or 2g+1)
+// and its neighbour A on the side of the point, with a weight of B of 0.5 +- eps:  out = (B - A) * t + A.
+// axis_fetch() replays that literally.  The two texels are {2g, 2g+1} with ONE exception that the reference really
+// has: for g = 0 and sizes N with fl(fl(1/N) * N) == pred(1.0f) (41, 47, 55, 61, 82, ...), the neighbour coordinate
+// 0.99999994 + 1 rounds to 2.0, so A is texel 2 and texel 1 is skipped (tests/test_npot_weights.py pins this down
+// for every size the device supports).  Either way level l+k of a tile depends only on texels [2g, 2g+2] of the
+// previous level, so one CTA can take a 64 x 64 (32 x 16 x 16) source tile through up to 6 (4) levels in shared
+// memory; the host cuts a launch short where texel 2 would lie outside a 2-texel-wide remainder.  Partial tiles at
+// the image border are masked.  Every level is re-decoded from its stored (quantised) bits.
+// ------------------------------------------------------------------------------------------------------
+struct axis_f {
+	float t;       // weight of B
+	uint32_t a, b; // texel indices of A (outside) and B (active) in the source level
+};
+// Same values as the literal replay in generic_texel(), computed without the quarter-rate XU pipe and without fmodf:
+// for 0 <= x < 2^23, x + 2^23 rounded toward zero holds floor(x) in its mantissa (the codecs use the same identity),
+// float(u) for u < 2^23 is (2^23 | u) - 2^23, and wrap(coord, 1) is the identity for 0 <= coord < 1 (always the case:
+// (2g+1) * fl(1/N) < 1 for g < N / 2); anything else takes the literal path.
+__device__ __forceinline__ axis_f axis_fetch(uint32_t g, float inv_prev, float fdim, float fdim_excl) {
+	constexpr float MAGIC = 8388608.0f;
+	const uint32_t n = g * 2u + 1u;
+	const float fn = n < 0x800000u ? __fsub_rn(__uint_as_float(0x4B000000u | n), MAGIC) : __uint2float_rn(n);
+	const float coord = __fmul_rn(fn, inv_prev);                             // mip_map_minify.hpp:106
+	const float m = __fmul_rn(coord, fdim);                                  // host_image.hpp:168-172, 875
+	axis_f r;
+	if (coord >= 0.0f && coord < 1.0f && m < 4194304.0f) {
+		const float fl = __fsub_rn(__fadd_rz(m, MAGIC), MAGIC);              // floorf(m), m >= 0
+		const float frac = __fsub_rn(m, fl);                                 // const_math.hpp:308-313
+		const bool lo = frac < 0.5f;
+		r.t = lo ? __fadd_rn(frac, 0.5f) : __fsub_rn(1.5f, frac);
+		const float mb = m > fdim_excl ? fdim_excl : m;
+		float ma = __fadd_rn(m, lo ? -1.0f : 1.0f);
+		ma = ma > fdim_excl ? fdim_excl : (ma < 0.0f ? 0.0f : ma);
+		r.b = __float_as_uint(__fadd_rz(mb, MAGIC)) & 0x7FFFFFu;
+		r.a = __float_as_uint(__fadd_rz(ma, MAGIC)) & 0x7FFFFFu;
+	} else {
+		const float scaled = __fmul_rn(wrap01(coord), fdim);
+		const float frac = __fsub_rn(scaled, floorf(scaled));
+		r.t = frac < 0.5f ? __fadd_rn(frac, 0.5f) : __fsub_rn(1.5f, frac);
+		const float ma = __fadd_rn(m, frac < 0.5f ? -1.0f : 1.0f);
+		r.b = (uint32_t)__float2ll_rz(m > fdim_excl ? fdim_excl : (m < 0.0f ? 0.0f : m));
+		r.a = (uint32_t)__float2ll_rz(ma > fdim_excl ? fdim_excl : (ma < 0.0f ? 0.0f : ma));
+	}
+	return r;
+}
+
+template <int D> struct tile_geo;
+template <> struct tile_geo<2> { static constexpr int TX = FLMIP_TILE2D_X, TY = FLMIP_TILE2D_Y, TZ = 1, MAXLEV = FLMIP_TILE_MAX_LEVELS; };
+template <> struct tile_geo<3> { static constexpr int TX = FLMIP_TILE3D_X, TY = FLMIP_TILE3D_Y, TZ = FLMIP_TILE3D_Z, MAXLEV = FLMIP_TILE3D_MAX_LEVELS; };
+
+// reduce the 2^D raw texels of one fetch (index bit d = 0: texel A of axis d, 1: texel B) to one stored texel: x, then y, then z
+template <uint32_t EK, int CH, int D, int NW>
+__device__ __forceinline__ void tile_reduce_block(const uint32_t (&raw)[1 << D][NW], const axis_f (&af)[D], uint32_t no_double, uint32_t (&out)[NW]) {
+	using C = Codec<EK>;
+	uint32_t v[1 << D][CH];
+#pragma unroll
+	for (int k = 0; k < (1 << D); ++k)
+#pragma unroll
+		for (int i = 0; i < CH; ++i) v[k][i] = C::dec_at(raw[k], i);
+#pragma unroll
+	for (int d = 0; d < D; ++d) {
+		const int step = 1 << d;
+#pragma unroll
+		for (int k = 0; k < (1 << D); k += 2 * step)
+#pragma unroll
+			for (int i = 0; i < CH; ++i) v[k][i] = C::lerp_t(v[k][i], v[k + step][i], af[d].t);
+	}
+	if constexpr ((CH * C::BYTES) % 4 == 0) {
+		C::template enc_pack<CH>(v[0], out, no_double);
+	} else {
+#pragma unroll
+		for (int w = 0; w < NW; ++w) out[w] = 0u;
+#pragma unroll
+		for (int i = 0; i < CH; ++i) put_elem<C::BYTES>(out, i, C::enc(v[0][i], no_double));
+	}
+}
+
+template <uint32_t EK, int CH, int D>
+__device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
+	using C = Codec<EK>;
+	using G = tile_geo<D>;
+	constexpr int BPP = C::BYTES * CH;
+	using IO = TexelIO<BPP>;
+	constexpr int NW = IO::NW;
+	constexpr int N1 = (G::TX / 2) * (G::TY / 2) * (D == 3 ? G::TZ / 2 : 1); // texels of level 1 of a tile
+	constexpr int N2 = N1 >> D;
+	constexpr int THREADS = 256;
+	__shared__ uint32_t buf0[N1 * NW];
+	__shared__ uint32_t buf1[N2 * NW];
+
+	const uint32_t t = threadIdx.x;
+	uint32_t tile = blockIdx.x;
+	uint32_t ti[3];
+	ti[0] = tile % P.tiles[0]; tile /= P.tiles[0];
+	ti[1] = tile % P.tiles[1]; tile /= P.tiles[1];
+	ti[2] = 0;
+	if constexpr (D == 3) { ti[2] = tile % P.tiles[2]; tile /= P.tiles[2]; }
+	const uint32_t layer = tile;
+	uint8_t* const base = reinterpret_cast<uint8_t*>(P.base);
+
+	// ---- level 1: straight from global memory (each warp reads whole 2 * BPP * 32 byte row segments) -------------
+	{
+		constexpr int EX = G::TX / 2, EY = G::TY / 2; // extents of level 1 of the tile
+		constexpr int PER_THREAD = N1 / THREADS;
+		constexpr int U = ((1 << D) * NW >= 16) ? 2 : 4; // outputs whose loads are in flight together
+		static_assert(PER_THREAD % U == 0, "unroll");
+		const uint8_t* const src = base + P.level_off[0] + (uint64_t)layer * P.slice[0];
+		uint8_t* const dst = base + P.level_off[1] + (uint64_t)layer * P.slice[1];
+		const uint32_t W0 = P.dim[0][0], H0 = P.dim[0][1];
+		const uint32_t W1 = P.dim[1][0], H1 = P.dim[1][1], D1 = P.dim[1][2];
+		// o = t + c * THREADS: the x index (and in 3D the y index) of a thread's outputs does not depend on c
+		static_assert(THREADS % EX == 0 && (D < 3 || THREADS % (EX * EY) == 0), "loop-invariant axes");
+		constexpr int INV = (D == 3 ? 2 : 1); // number of loop-invariant axes
+		axis_f fix[INV];
+		fix[0] = axis_fetch(min(ti[0] * EX + t % EX, W1 - 1u), P.inv_prev[0][0], P.fdim[0][0], P.fdim_excl[0][0]);
+		if constexpr (D == 3) fix[1] = axis_fetch(min(ti[1] * EY + (t / EX) % EY, H1 - 1u), P.inv_prev[0][1], P.fdim[0][1], P.fdim_excl[0][1]);
+#pragma unroll 1
+		for (int c = 0; c < PER_THREAD; c += U) {
+			uint32_t raw[U][1 << D][NW];
+			uint32_t g[U][3], o[U];
+			float wt[U][D];
+			bool ok[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				o[u] = t + (uint32_t)(c + u) * THREADS;
+				const uint32_t ox = o[u] % EX, oy = (o[u] / EX) % EY, oz = o[u] / (EX * EY);
+				g[u][0] = ti[0] * EX + ox; g[u][1] = ti[1] * EY + oy; g[u][2] = (D == 3 ? ti[2] * (G::TZ / 2) + oz : 0u);
+				ok[u] = g[u][0] < W1 && g[u][1] < H1 && (D < 3 || g[u][2] < D1);
+				if (ok[u]) {
+					uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+#pragma unroll
+					for (int d = 0; d < D; ++d) {
+						const axis_f f = d < INV ? fix[d < INV ? d : 0] : axis_fetch(g[u][d], P.inv_prev[0][d], P.fdim[0][d], P.fdim_excl[0][d]);
+						wt[u][d] = f.t; s[d][0] = f.a; s[d][1] = f.b;
+					}
+#pragma unroll
+					for (int k = 0; k < (1 << D); ++k) {
+						const uint64_t sx = s[0][k & 1], sy = s[1][(k >> 1) & 1], sz = s[2][(k >> 2) & 1];
+						IO::template load<false>(src + ((sz * H0 + sy) * W0 + sx) * BPP, raw[u][k]);
+					}
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (ok[u]) {
+					axis_f af[D];
+#pragma unroll
+					for (int d = 0; d < D; ++d) af[d].t = wt[u][d];
+					uint32_t out[NW];
+					tile_reduce_block<EK, CH, D, NW>(raw[u], af, P.no_double, out);
+					IO::store(dst + (((uint64_t)g[u][2] * H1 + g[u][1]) * W1 + g[u][0]) * BPP, out);
+#pragma unroll
+					for (int w = 0; w < NW; ++w) buf0[o[u] * NW + w] = out[w];
+				}
+			}
+		}
+	}
+	// ---- levels 2 .. nlev: shared memory ping-pong, every level also written to global ----------------------------
+#pragma unroll 1
+	for (uint32_t k = 2; k <= P.nlev; ++k) {
+		__syncthreads();
+		const uint32_t* const in = (k & 1u) ? buf1 : buf0;
+		uint32_t* const outb = (k & 1u) ? buf0 : buf1;
+		const uint32_t ex = G::TX >> k, ey = G::TY >> k, ez = (D == 3 ? G::TZ >> k : 1u); // extents of level k of the tile
+		const uint32_t n = ex * ey * ez;
+		if (t < n) {
+			const uint32_t ox = t % ex, oy = (t / ex) % ey, oz = t / (ex * ey);
+			const uint32_t g[3] = { ti[0] * ex + ox, ti[1] * ey + oy, (D == 3 ? ti[2] * ez + oz : 0u) };
+			if (g[0] < P.dim[k][0] && g[1] < P.dim[k][1] && (D < 3 || g[2] < P.dim[k][2])) {
+				const uint32_t pe[3] = { 2u * ex, 2u * ey, 2u * ez }; // extents of level k - 1 of the tile
+				axis_f af[D];
+				uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+#pragma unroll
+				for (int d = 0; d < D; ++d) {
+					af[d] = axis_fetch(g[d], P.inv_prev[k - 1][d], P.fdim[k - 1][d], P.fdim_excl[k - 1][d]);
+					// tile-local indices in level k - 1 (the host guarantees they lie inside the tile's remainder)
+					s[d][0] = min(af[d].a - ti[d] * pe[d], pe[d] - 1u);
+					s[d][1] = min(af[d].b - ti[d] * pe[d], pe[d] - 1u);
+				}
+				uint32_t raw[1 << D][NW];
+#pragma unroll
+				for (int b = 0; b < (1 << D); ++b) {
+					const uint32_t idx = ((s[2][(b >> 2) & 1] * pe[1] + s[1][(b >> 1) & 1]) * pe[0] + s[0][b & 1]) * NW;
+#pragma unroll
+					for (int w = 0; w < NW; ++w) raw[b][w] = in[idx + w];
+				}
+				uint32_t out[NW];
+				tile_reduce_block<EK, CH, D, NW>(raw, af, P.no_double, out);
+				uint8_t* const dst = base + P.level_off[k] + (uint64_t)layer * P.slice[k];
+				IO::store(dst + (((uint64_t)g[2] * P.dim[k][1] + g[1]) * P.dim[k][0] + g[0]) * BPP, out);
+#pragma unroll
+				for (int w = 0; w < NW; ++w) outb[t * NW + w] = out[w];
+			}
+		}
+	}
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 	x += 0x9E3779B97F4A7C15ull;
 	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -1151,4 +1353,27 @@ FLMIP_FAST_KERNELS_FOR_KIND(8)
 FLMIP_FAST_KERNELS_FOR_KIND(9)
 FLMIP_FAST_KERNELS_FOR_KIND(10)
 FLMIP_FAST_KERNELS_FOR_KIND(11)
+#endif
+
+#define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
+	extern "C" __global__ void __launch_bounds__(256) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
+		tile_body<K, CHN, D>(P);                                                                                                 \
+	}
+#define FLMIP_TILE_KERNELS_FOR_KIND(K) \
+	FLMIP_TILE_KERNEL(2, K, 1) FLMIP_TILE_KERNEL(2, K, 2) FLMIP_TILE_KERNEL(2, K, 4) FLMIP_TILE_KERNEL(3, K, 1) FLMIP_TILE_KERNEL(3, K, 2) FLMIP_TILE_KERNEL(3, K, 4)
+#ifdef FLMIP_DEV_ONLY
+FLMIP_TILE_KERNEL(2, 2, 4) FLMIP_TILE_KERNEL(2, 1, 4) FLMIP_TILE_KERNEL(3, 0, 1) FLMIP_TILE_KERNEL(2, 0, 4) FLMIP_TILE_KERNEL(3, 1, 4)
+#else
+FLMIP_TILE_KERNELS_FOR_KIND(0)
+FLMIP_TILE_KERNELS_FOR_KIND(1)
+FLMIP_TILE_KERNELS_FOR_KIND(2)
+FLMIP_TILE_KERNELS_FOR_KIND(3)
+FLMIP_TILE_KERNELS_FOR_KIND(4)
+FLMIP_TILE_KERNELS_FOR_KIND(5)
+FLMIP_TILE_KERNELS_FOR_KIND(6)
+FLMIP_TILE_KERNELS_FOR_KIND(7)
+FLMIP_TILE_KERNELS_FOR_KIND(8)
+FLMIP_TILE_KERNELS_FOR_KIND(9)
+FLMIP_TILE_KERNELS_FOR_KIND(10)
+FLMIP_TILE_KERNELS_FOR_KIND(11)
 #endif

@@ -60,6 +60,28 @@ struct flmip_fast_params {
 	uint32_t stages;        // depth of the TMA tile ring in shared memory (<= FLMIP_MAX_STAGES)
 };
 
+// multi-level tile kernel, any size (NPOT capable): one CTA reduces one source tile of level [0] through `nlev` levels.
+// Source tile = 64 x 64 texels (2D, up to 6 levels) or 32 x 16 x 16 texels (3D, up to 4 levels).
+#define FLMIP_TILE_MAX_LEVELS 6u
+#define FLMIP_TILE2D_X 64u
+#define FLMIP_TILE2D_Y 64u
+#define FLMIP_TILE3D_X 32u
+#define FLMIP_TILE3D_Y 16u
+#define FLMIP_TILE3D_Z 16u
+#define FLMIP_TILE3D_MAX_LEVELS 4u
+struct flmip_tile_params {
+	uint64_t base;
+	uint64_t level_off[FLMIP_TILE_MAX_LEVELS + 1]; // [0] = source level, [k] = k-th produced level
+	uint64_t slice[FLMIP_TILE_MAX_LEVELS + 1];     // bytes of one layer
+	uint32_t dim[FLMIP_TILE_MAX_LEVELS + 1][3];    // texels (z = 1 for 2D)
+	// sampler constants of produced level k, taken from its source level k - 1 (index k - 1):
+	float inv_prev[FLMIP_TILE_MAX_LEVELS][3];  // 1.0f / float(dim)  (device_image.cpp:311-312)
+	float fdim[FLMIP_TILE_MAX_LEVELS][3];      // float(dim)         (host_image.cpp:96-101)
+	float fdim_excl[FLMIP_TILE_MAX_LEVELS][3]; // nextafterf(fdim,0) (host_image.cpp:102-107)
+	uint32_t tiles[3];                         // source tiles per layer
+	uint32_t nlev, layers, no_double;
+};
+
 struct flmip_fill_params {
 	uint64_t dst;             // device address of level 0 of the first layer to fill
 	uint64_t elems_per_layer; // texels * channels

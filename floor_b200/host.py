@@ -144,10 +144,10 @@ class device_queue:
 class device_image:
     def __init__(self, cqueue: device_queue, image_dim, image_type: int, data=None,
                  flags: int = MEMORY_FLAG.HOST_READ_WRITE, mip_level_limit: int = 0, no_double: bool = False,
-                 force_generic: bool = False, units: bool | None = None):
-        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, LevelInfo
+                 force_generic: bool = False, units: bool | None = None, force_tiled: bool = False):
+        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED, LevelInfo
         self.dev = cqueue.dev
-        self._create_kw = {"no_double": no_double, "force_generic": force_generic, "units": units}
+        self._create_kw = {"no_double": no_double, "force_generic": force_generic, "units": units, "force_tiled": force_tiled}
         dim = list(image_dim) + [0] * (4 - len(image_dim))
         # device_image::handle_image_type (device_image.hpp:70-91)
         if flags & MEMORY_FLAG.GENERATE_MIP_MAPS:
@@ -156,6 +156,7 @@ class device_image:
         self._handle = ctypes.c_void_p()
         cflags = (IMAGE_NO_DOUBLE if no_double else 0) | (IMAGE_FORCE_GENERIC if force_generic else 0)
         cflags |= 0 if units is None else (IMAGE_UNITS_ALWAYS if units else IMAGE_UNITS_NEVER)
+        cflags |= IMAGE_FORCE_TILED if force_tiled else 0
         _check(_L().flmip_image_create(self.dev.index, image_type, _u32x(dim, 4), mip_level_limit, cflags,
                                        ctypes.byref(self._handle)))
         n = ctypes.c_uint32()

@@ -30,9 +30,10 @@ extern "C" {
 
 /* flags of flmip_image_create */
 #define FLMIP_IMAGE_NO_DOUBLE 1u     /* FLOOR_DEVICE_NO_DOUBLE encoders for 16-bit normalized formats (host_image.hpp:398-402) */
-#define FLMIP_IMAGE_FORCE_GENERIC 2u /* never use the single-pass kernel (validation / A-B timing) */
+#define FLMIP_IMAGE_FORCE_GENERIC 2u /* only the literal one-launch-per-level kernel (validation / A-B timing) */
 #define FLMIP_IMAGE_UNITS_ALWAYS 4u  /* single-pass kernel: schedule 2x2(x2)-tile units whenever the tile grid allows it */
 #define FLMIP_IMAGE_UNITS_NEVER 8u   /* single-pass kernel: always schedule single tiles (default: by image size) */
+#define FLMIP_IMAGE_FORCE_TILED 16u  /* never use the persistent single-pass kernel: multi-level tile kernel for every level (validation / A-B timing) */
 
 typedef struct flmip_image_s* flmip_image;
 typedef void* flmip_stream; /* CUstream */

@@ -73,14 +73,74 @@ def test_single_pass_3d_all_formats(gpu_ctx, oracle_mod, fmt):
 
 @pytest.mark.parametrize("fmt", ALL_FORMATS)
 def test_general_path_all_formats(gpu_ctx, oracle_mod, fmt):
-    """NPOT / small / 1D images take the general per-level kernel"""
+    """NPOT / small images take the multi-level tile kernel, 1D images the literal per-level kernel; the literal kernel
+    (force_generic) must agree with both"""
     for base, dim in [(T.IMAGE_2D, (37, 21)), (T.IMAGE_2D, (100, 60)), (T.IMAGE_2D_ARRAY, (20, 12, 3)), (T.IMAGE_3D, (12, 10, 6)),
                       (T.IMAGE_1D, (33,)), (T.IMAGE_1D_ARRAY, (64, 2)), (T.IMAGE_2D, (16, 16))]:
         t = base | fmt | M
         l0 = oracle_mod.fill_synthetic(dim, t, 300 + (fmt & 0xFFFF))
         got, plan = gpu_chain(gpu_ctx, l0, dim, t)
         assert not plan["single_pass"]
-        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4), t, dim, "general")
+        want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4)
+        assert_same(got, want, t, dim, "general")
+        lit, plan = gpu_chain(gpu_ctx, l0, dim, t, force_generic=True)
+        assert plan["launches"] == sum(1 for l in range(1, oracle_mod.mip_level_count(dim, t)) if oracle_mod.level_size(dim, t, l))
+        assert_same(lit, want, t, dim, "literal general kernel")
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_tile_kernel_all_formats(gpu_ctx, oracle_mod, fmt):
+    """multi-level tile kernel (flmip_tile2d / 3d): NPOT sizes with partial border tiles, odd levels, several launches per chain
+    (more than 6 / 4 levels), arrays, cubes, and power-of-two images forced onto it"""
+    cases = [(T.IMAGE_2D, (333, 129), {}), (T.IMAGE_2D, (1000, 70), {}), (T.IMAGE_2D_ARRAY, (130, 67, 3), {}), (T.IMAGE_CUBE, (96, 96), {}),
+             (T.IMAGE_3D, (70, 33, 18), {}), (T.IMAGE_3D, (65, 40, 100), {}), (T.IMAGE_2D, (256, 128), {"force_tiled": True}),
+             (T.IMAGE_3D, (64, 32, 32), {"force_tiled": True}), (T.IMAGE_2D, (64, 4), {}), (T.IMAGE_2D, (5, 3), {}),
+             # texel-2 quirk sizes (tests/test_npot_weights.py) at level 0 and, via 2624 = 41 << 6 / 188 = 47 << 2, deep inside a tile
+             (T.IMAGE_2D, (41, 47), {}), (T.IMAGE_2D, (2624, 188), {}), (T.IMAGE_3D, (55, 61, 41), {}), (T.IMAGE_3D, (328, 94, 82), {})]
+    for base, dim, kw in cases:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 600 + (fmt & 0xFFFF))
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t, **kw)
+        assert not plan["single_pass"], (dim, plan)
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4), t, dim, "tile kernel")
+        if it.bits_per_channel(t) == 16 and (t & T.FLAG_NORMALIZED):
+            got, _ = gpu_chain(gpu_ctx, l0, dim, t, no_double=True, **kw)
+            assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, no_double=True, threads=4), t, dim, "tile kernel, no_double")
+
+
+def test_tile_kernel_launch_plan_and_large_npot(gpu_ctx, oracle_mod):
+    """3840 x 2160 RGBA8 (12 levels) = 2 launches; 64 layers of 1920 x 1080 RGBA16F; a 300 x 200 x 100 volume"""
+    for base, fmt, dim, launches in [(T.IMAGE_2D, T.RGBA8, (3840, 2160), 2), (T.IMAGE_2D_ARRAY, T.RGBA16F, (1920, 1080, 6), 2),
+                                     (T.IMAGE_3D, T.R32F, (300, 200, 100), 2), (T.IMAGE_2D, T.R8, (4097, 33), 1), (T.IMAGE_2D, T.RG8, (5000, 3000), 2)]:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 77)
+        got, plan = gpu_chain(gpu_ctx, l0, dim, t)
+        assert plan["launches"] == launches and not plan["single_pass"], (dim, plan)
+        assert_same(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=os.cpu_count() or 8), t, dim, "tile kernel, large")
+
+
+def test_regenerate_from_dirty_level(gpu_ctx, oracle_mod):
+    """flmip_mip_chain_generate_from: overwrite level 2, regenerate only the levels below it (tile kernel from level 2)"""
+    ctx, dev, q = gpu_ctx
+    for dim, bt in [((512, 256), T.IMAGE_2D | T.RGBA8), ((300, 200), T.IMAGE_2D | T.RGBA16F), ((64, 64, 64), T.IMAGE_3D | T.R32F)]:
+        t = bt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 88)
+        img = ctx.create_image(q, dim, t)
+        img.upload_levels(q, l0, 0, 0)
+        img.generate_mip_map_chain(q)
+        ldim = oracle_mod.level_dim(dim, t, 2)
+        sub = tuple(d for d in ldim[: len(dim)])
+        new2 = oracle_mod.fill_synthetic(sub, t, 89)
+        img.upload_levels(q, new2, 2, 2)
+        img.enqueue_mip_map_chain(q, first_level=2)
+        q.finish()
+        got = img.download_levels(q)
+        img.destroy()
+        want_top = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4)
+        o2 = oracle_mod.level_offset(dim, t, 2)
+        want_tail = oracle_mod.generate_mip_map_chain(new2, sub, t, threads=4)
+        assert np.array_equal(got[:o2], want_top[:o2])
+        assert_same(got[o2:], want_tail[: got.size - o2], t, dim, "regenerated tail")
 
 
 def test_general_equals_single_pass(gpu_ctx, oracle_mod):

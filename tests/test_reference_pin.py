@@ -114,7 +114,9 @@ FORMATS = [T.R8, T.RG8, T.RGB8, T.RGBA8, T.R16, T.RG16, T.RGBA16, T.R8I_NORM, T.
            T.R16F, T.RG16F, T.RGB16F, T.RGBA16F, T.R32F, T.RG32F, T.RGB32F, T.RGBA32F]
 SHAPES = [(T.IMAGE_2D, (64, 64)), (T.IMAGE_2D, (20, 12)), (T.IMAGE_2D, (37, 5)), (T.IMAGE_2D, (129, 67)), (T.IMAGE_2D, (64, 4)),
           (T.IMAGE_2D_ARRAY, (16, 8, 3)), (T.IMAGE_2D_ARRAY, (11, 23, 2)), (T.IMAGE_3D, (16, 16, 16)), (T.IMAGE_3D, (12, 10, 6)),
-          (T.IMAGE_3D, (7, 33, 5)), (T.IMAGE_CUBE, (8, 8)), (T.IMAGE_CUBE_ARRAY, (6, 6, 2))]
+          (T.IMAGE_3D, (7, 33, 5)), (T.IMAGE_CUBE, (8, 8)), (T.IMAGE_CUBE_ARRAY, (6, 6, 2)),
+          # sizes where the reference's linear fetch for destination texel 0 reads texels 0 and 2 (tests/test_npot_weights.py)
+          (T.IMAGE_2D, (41, 47)), (T.IMAGE_2D, (83, 164)), (T.IMAGE_3D, (55, 61, 41)), (T.IMAGE_2D_ARRAY, (97, 94, 2))]
 
 
 @pytest.mark.parametrize("fmt", FORMATS)
