@@ -560,6 +560,9 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 		T.tiles[2] = im.dc == 3 ? (T.dim[0][2] + FLMIP_TILE3D_Z - 1u) / FLMIP_TILE3D_Z : 1u;
 		T.layers = im.layers;
 		T.no_double = im.no_double;
+		for (uint32_t k = 2; k <= T.nlev; ++k)
+			for (uint32_t d = 0; d < im.dc; ++d)
+				if (axis_reads_texel_2(im.levels[s + k - 1u].dim[d])) T.block_sync = 1u;
 		void* args[] = { &T };
 		const int rc = launch(fn, (uint64_t)T.tiles[0] * T.tiles[1] * T.tiles[2] * im.layers, 256, 0, stream, args);
 		if (rc != FLMIP_OK) return rc;

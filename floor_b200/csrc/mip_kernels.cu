@@ -76,6 +76,20 @@ __device__ __forceinline__ f32x2_t mul2_rz(f32x2_t a, f32x2_t b) {
 	return r;
 }
 
+// RN(a * b) that ptxas cannot merge with a following add: it contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (unlike
+// the scalar mul.rn / add.rn, which are never fused; --fmad=false does not stop it, and it folds a literal -0 addend), which
+// would round once where the reference rounds product and sum separately.  fma(a, b, -0) == RN(a * b) bit for bit (a -0
+// addend keeps the sign of a zero product); the -0 comes from a special register ptxas cannot reason about.
+__device__ __forceinline__ uint32_t opaque_neg_zero() {
+	uint32_t r;
+	asm("{\n\t.reg .u32 t;\n\tmov.u32 t, %%nsmid;\n\tshr.u32 t, t, 31;\n\tor.b32 %0, t, 0x80000000;\n\t}" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ f32x2_t mul2_sep(f32x2_t a, f32x2_t b) {
+	const uint32_t nz = opaque_neg_zero();
+	return fma2_rn(a, b, pk2(nz, nz));
+}
+
 // ------------------------------------------------------------------------------------------------------
 // element codecs
 // ------------------------------------------------------------------------------------------------------
@@ -211,7 +225,8 @@ template <uint32_t EK> struct Codec {
 	}
 	static __device__ __forceinline__ f32x2_t lerp_half2(f32x2_t a, f32x2_t b) {
 		static_assert(!IS_INT, "float formats only");
-		if constexpr (EK == FLMIP_EK_F32) return add2_rn(mul2_rn(sub2_rn(b, a), splat2(0.5f)), a);
+		// fp32 storage: product and sum are rounded separately ((b - a) * 0.5 can be an inexact subnormal), see mul2_sep()
+		if constexpr (EK == FLMIP_EK_F32) return add2_rn(mul2_sep(sub2_rn(b, a), splat2(0.5f)), a);
 		else return fma2_rn(sub2_rn(b, a), splat2(0.5f), a);
 	}
 	// storage bits of two elements; bits above the storage width are unspecified
@@ -1129,26 +1144,46 @@ template <> struct tile_geo<3> { static constexpr int TX = FLMIP_TILE3D_X, TY = 
 template <uint32_t EK, int CH, int D, int NW>
 __device__ __forceinline__ void tile_reduce_block(const uint32_t (&raw)[1 << D][NW], const axis_f (&af)[D], uint32_t no_double, uint32_t (&out)[NW]) {
 	using C = Codec<EK>;
-	uint32_t v[1 << D][CH];
+	if constexpr (!C::IS_INT && (CH % 2) == 0 && ((CH * C::BYTES) % 4) == 0) {
+		// float formats, channel pairs: packed fp32 (FADD2 / FMUL2, per-lane IEEE rounding) -- (b - a) * t + a in three roundings
+		f32x2_t p[1 << D][CH / 2];
 #pragma unroll
-	for (int k = 0; k < (1 << D); ++k)
+		for (int k = 0; k < (1 << D); ++k)
 #pragma unroll
-		for (int i = 0; i < CH; ++i) v[k][i] = C::dec_at(raw[k], i);
+			for (int j = 0; j < CH / 2; ++j) p[k][j] = C::dec2_at(raw[k], 2 * j, 2 * j + 1);
 #pragma unroll
-	for (int d = 0; d < D; ++d) {
-		const int step = 1 << d;
+		for (int d = 0; d < D; ++d) {
+			const int step = 1 << d;
+			const f32x2_t t2 = splat2(af[d].t);
+			// t is not 0.5 here, so the product is not exact: it has to be rounded on its own (mul2_sep)
 #pragma unroll
-		for (int k = 0; k < (1 << D); k += 2 * step)
+			for (int k = 0; k < (1 << D); k += 2 * step)
 #pragma unroll
-			for (int i = 0; i < CH; ++i) v[k][i] = C::lerp_t(v[k][i], v[k + step][i], af[d].t);
-	}
-	if constexpr ((CH * C::BYTES) % 4 == 0) {
-		C::template enc_pack<CH>(v[0], out, no_double);
+				for (int j = 0; j < CH / 2; ++j) p[k][j] = add2_rn(mul2_sep(sub2_rn(p[k + step][j], p[k][j]), t2), p[k][j]);
+		}
+		C::template enc_pack2<CH / 2>(p[0], out, no_double);
 	} else {
+		uint32_t v[1 << D][CH];
 #pragma unroll
-		for (int w = 0; w < NW; ++w) out[w] = 0u;
+		for (int k = 0; k < (1 << D); ++k)
 #pragma unroll
-		for (int i = 0; i < CH; ++i) put_elem<C::BYTES>(out, i, C::enc(v[0][i], no_double));
+			for (int i = 0; i < CH; ++i) v[k][i] = C::dec_at(raw[k], i);
+#pragma unroll
+		for (int d = 0; d < D; ++d) {
+			const int step = 1 << d;
+#pragma unroll
+			for (int k = 0; k < (1 << D); k += 2 * step)
+#pragma unroll
+				for (int i = 0; i < CH; ++i) v[k][i] = C::lerp_t(v[k][i], v[k + step][i], af[d].t);
+		}
+		if constexpr ((CH * C::BYTES) % 4 == 0) {
+			C::template enc_pack<CH>(v[0], out, no_double);
+		} else {
+#pragma unroll
+			for (int w = 0; w < NW; ++w) out[w] = 0u;
+#pragma unroll
+			for (int i = 0; i < CH; ++i) put_elem<C::BYTES>(out, i, C::enc(v[0][i], no_double));
+		}
 	}
 }
 
@@ -1164,8 +1199,9 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 	constexpr int THREADS = 256;
 	__shared__ uint32_t buf0[N1 * NW];
 	__shared__ uint32_t buf1[N2 * NW];
+	__shared__ uint32_t buf2[(N2 >> D) * NW]; // 2D: level 3 must not land in buf0 while other warps still read level 1 from it
 
-	const uint32_t t = threadIdx.x;
+	const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
 	uint32_t tile = blockIdx.x;
 	uint32_t ti[3];
 	ti[0] = tile % P.tiles[0]; tile /= P.tiles[0];
@@ -1176,16 +1212,18 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 	uint8_t* const base = reinterpret_cast<uint8_t*>(P.base);
 
 	// ---- level 1: straight from global memory (each warp reads whole 2 * BPP * 32 byte row segments) -------------
+	// 2D: warp w owns rows 4w .. 4w+3 of level 1 (so that levels 2 and 3 stay inside the warp); 3D: o = t + c * 256
 	{
 		constexpr int EX = G::TX / 2, EY = G::TY / 2; // extents of level 1 of the tile
 		constexpr int PER_THREAD = N1 / THREADS;
 		constexpr int U = ((1 << D) * NW >= 16) ? 2 : 4; // outputs whose loads are in flight together
 		static_assert(PER_THREAD % U == 0, "unroll");
+		static_assert(D == 3 || (EX == 32 && PER_THREAD == 4), "2D mapping: one row of 32 outputs per warp and step");
 		const uint8_t* const src = base + P.level_off[0] + (uint64_t)layer * P.slice[0];
 		uint8_t* const dst = base + P.level_off[1] + (uint64_t)layer * P.slice[1];
 		const uint32_t W0 = P.dim[0][0], H0 = P.dim[0][1];
 		const uint32_t W1 = P.dim[1][0], H1 = P.dim[1][1], D1 = P.dim[1][2];
-		// o = t + c * THREADS: the x index (and in 3D the y index) of a thread's outputs does not depend on c
+		// the x index (and in 3D the y index) of a thread's outputs does not depend on the step c
 		static_assert(THREADS % EX == 0 && (D < 3 || THREADS % (EX * EY) == 0), "loop-invariant axes");
 		constexpr int INV = (D == 3 ? 2 : 1); // number of loop-invariant axes
 		axis_f fix[INV];
@@ -1199,7 +1237,7 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 			bool ok[U];
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
-				o[u] = t + (uint32_t)(c + u) * THREADS;
+				o[u] = (D == 2 ? (warp * PER_THREAD + (uint32_t)(c + u)) * 32u + lane : t + (uint32_t)(c + u) * THREADS);
 				const uint32_t ox = o[u] % EX, oy = (o[u] / EX) % EY, oz = o[u] / (EX * EY);
 				g[u][0] = ti[0] * EX + ox; g[u][1] = ti[1] * EY + oy; g[u][2] = (D == 3 ? ti[2] * (G::TZ / 2) + oz : 0u);
 				ok[u] = g[u][0] < W1 && g[u][1] < H1 && (D < 3 || g[u][2] < D1);
@@ -1232,42 +1270,67 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 			}
 		}
 	}
+
 	// ---- levels 2 .. nlev: shared memory ping-pong, every level also written to global ----------------------------
-#pragma unroll 1
-	for (uint32_t k = 2; k <= P.nlev; ++k) {
-		__syncthreads();
-		const uint32_t* const in = (k & 1u) ? buf1 : buf0;
-		uint32_t* const outb = (k & 1u) ? buf0 : buf1;
+	// one output texel of level k: tile-local coordinates (ox, oy, oz), slot `oi` of the level's buffer
+	auto produce = [&](uint32_t k, const uint32_t* in, uint32_t* outb, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t oi) {
 		const uint32_t ex = G::TX >> k, ey = G::TY >> k, ez = (D == 3 ? G::TZ >> k : 1u); // extents of level k of the tile
-		const uint32_t n = ex * ey * ez;
-		if (t < n) {
-			const uint32_t ox = t % ex, oy = (t / ex) % ey, oz = t / (ex * ey);
-			const uint32_t g[3] = { ti[0] * ex + ox, ti[1] * ey + oy, (D == 3 ? ti[2] * ez + oz : 0u) };
-			if (g[0] < P.dim[k][0] && g[1] < P.dim[k][1] && (D < 3 || g[2] < P.dim[k][2])) {
-				const uint32_t pe[3] = { 2u * ex, 2u * ey, 2u * ez }; // extents of level k - 1 of the tile
-				axis_f af[D];
-				uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+		const uint32_t g[3] = { ti[0] * ex + ox, ti[1] * ey + oy, (D == 3 ? ti[2] * ez + oz : 0u) };
+		if (g[0] < P.dim[k][0] && g[1] < P.dim[k][1] && (D < 3 || g[2] < P.dim[k][2])) {
+			const uint32_t pe[3] = { 2u * ex, 2u * ey, 2u * ez }; // extents of level k - 1 of the tile
+			axis_f af[D];
+			uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
 #pragma unroll
-				for (int d = 0; d < D; ++d) {
-					af[d] = axis_fetch(g[d], P.inv_prev[k - 1][d], P.fdim[k - 1][d], P.fdim_excl[k - 1][d]);
-					// tile-local indices in level k - 1 (the host guarantees they lie inside the tile's remainder)
-					s[d][0] = min(af[d].a - ti[d] * pe[d], pe[d] - 1u);
-					s[d][1] = min(af[d].b - ti[d] * pe[d], pe[d] - 1u);
-				}
-				uint32_t raw[1 << D][NW];
-#pragma unroll
-				for (int b = 0; b < (1 << D); ++b) {
-					const uint32_t idx = ((s[2][(b >> 2) & 1] * pe[1] + s[1][(b >> 1) & 1]) * pe[0] + s[0][b & 1]) * NW;
-#pragma unroll
-					for (int w = 0; w < NW; ++w) raw[b][w] = in[idx + w];
-				}
-				uint32_t out[NW];
-				tile_reduce_block<EK, CH, D, NW>(raw, af, P.no_double, out);
-				uint8_t* const dst = base + P.level_off[k] + (uint64_t)layer * P.slice[k];
-				IO::store(dst + (((uint64_t)g[2] * P.dim[k][1] + g[1]) * P.dim[k][0] + g[0]) * BPP, out);
-#pragma unroll
-				for (int w = 0; w < NW; ++w) outb[t * NW + w] = out[w];
+			for (int d = 0; d < D; ++d) {
+				af[d] = axis_fetch(g[d], P.inv_prev[k - 1][d], P.fdim[k - 1][d], P.fdim_excl[k - 1][d]);
+				// tile-local indices in level k - 1 (the host guarantees they lie inside the tile's remainder)
+				s[d][0] = min(af[d].a - ti[d] * pe[d], pe[d] - 1u);
+				s[d][1] = min(af[d].b - ti[d] * pe[d], pe[d] - 1u);
 			}
+			uint32_t raw[1 << D][NW];
+#pragma unroll
+			for (int b = 0; b < (1 << D); ++b) {
+				const uint32_t idx = ((s[2][(b >> 2) & 1] * pe[1] + s[1][(b >> 1) & 1]) * pe[0] + s[0][b & 1]) * NW;
+#pragma unroll
+				for (int w = 0; w < NW; ++w) raw[b][w] = in[idx + w];
+			}
+			uint32_t out[NW];
+			tile_reduce_block<EK, CH, D, NW>(raw, af, P.no_double, out);
+			uint8_t* const dst = base + P.level_off[k] + (uint64_t)layer * P.slice[k];
+			IO::store(dst + (((uint64_t)g[2] * P.dim[k][1] + g[1]) * P.dim[k][0] + g[0]) * BPP, out);
+#pragma unroll
+			for (int w = 0; w < NW; ++w) outb[oi * NW + w] = out[w];
+		}
+	};
+
+	if constexpr (D == 2) {
+		// Levels 2 and 3 read only what the same warp wrote (warp w: rows 4w..4w+3 of level 1, rows 2w, 2w+1 of level 2, row w
+		// of level 3), so a warp barrier is enough -- unless the launch contains a texel-2 fetch (P.block_sync), which may
+		// reach into the next warp's rows.  Levels 4 .. 6 (16 + 4 + 1 texels) are finished by warp 0 alone.
+		const uint32_t nlev = P.nlev;
+		const bool bs = P.block_sync != 0u;
+		if (nlev < 2u) return;
+		if (bs) __syncthreads(); else __syncwarp();
+		produce(2u, buf0, buf1, t & 15u, t >> 4, 0u, t);           // 16 x 16, slot = row-major index = t
+		if (nlev < 3u) return;
+		if (bs) __syncthreads(); else __syncwarp();
+		if (lane < 8u) produce(3u, buf1, buf2, lane, warp, 0u, warp * 8u + lane); // 8 x 8, row w by warp w
+		if (nlev < 4u) return;
+		__syncthreads();
+		if (warp != 0u) return;
+		if (lane < 16u) produce(4u, buf2, buf1, lane & 3u, lane >> 2, 0u, lane);
+		if (nlev < 5u) return;
+		__syncwarp();
+		if (lane < 4u) produce(5u, buf1, buf2, lane & 1u, lane >> 1, 0u, lane);
+		if (nlev < 6u) return;
+		__syncwarp();
+		if (lane == 0u) produce(6u, buf2, buf1, 0u, 0u, 0u, 0u);
+	} else {
+#pragma unroll 1
+		for (uint32_t k = 2; k <= P.nlev; ++k) {
+			__syncthreads();
+			const uint32_t ex = G::TX >> k, ey = G::TY >> k, ez = G::TZ >> k;
+			if (t < ex * ey * ez) produce(k, (k & 1u) ? buf1 : buf0, (k & 1u) ? buf0 : buf1, t % ex, (t / ex) % ey, t / (ex * ey), t);
 		}
 	}
 }

@@ -80,6 +80,7 @@ struct flmip_tile_params {
 	float fdim_excl[FLMIP_TILE_MAX_LEVELS][3]; // nextafterf(fdim,0) (host_image.cpp:102-107)
 	uint32_t tiles[3];                         // source tiles per layer
 	uint32_t nlev, layers, no_double;
+	uint32_t block_sync; // 1: some produced level >= 2 contains a texel-2 fetch (block barriers instead of warp barriers)
 };
 
 struct flmip_fill_params {

@@ -266,6 +266,24 @@ def test_adversarial_floats(gpu_ctx, oracle_mod):
     assert_same(got, oracle_mod.generate_mip_map_chain(f, dim, t, threads=8), t, dim, "adversarial fp32")
 
 
+def test_subnormal_ties_round_like_the_reference(gpu_ctx, oracle_mod):
+    """fp32 texels that are tiny multiples of 2^-149: (b - a) * 0.5 is then an inexact subnormal and a fused multiply-add would
+    round differently from the reference's separate product and sum (a = 2^-149, b = 2^-148 -> 2^-149, fused: 2^-148).  ptxas
+    contracts mul.rn.f32x2 + add.rn.f32x2 on its own, so the packed kernels multiply through mul2_sep().  All three kernels."""
+    rng = np.random.default_rng(12)
+    small = np.array([0, 1, 2, 3, 4, 5, 6, 7, 9, 11, 0x80000001, 0x80000002, 0x80000003, 0x80000005, 0x00800000, 0x00800001, 0x007FFFFF], np.uint32)
+    for base, fmt, dim in [(T.IMAGE_2D, T.RGBA32F, (128, 128)), (T.IMAGE_2D, T.R32F, (256, 128)), (T.IMAGE_2D, T.RG32F, (128, 128)),
+                           (T.IMAGE_3D, T.R32F, (64, 32, 32)), (T.IMAGE_3D, T.RGBA32F, (16, 16, 32)), (T.IMAGE_2D, T.RGBA32F, (100, 60)),
+                           (T.IMAGE_3D, T.RG32F, (20, 12, 10))]:
+        t = base | fmt | M
+        n = int(np.prod(dim)) * it.channel_count(t)
+        f = small[rng.integers(0, small.size, size=n)]
+        want = oracle_mod.generate_mip_map_chain(f, dim, t, threads=4)
+        for kw in ({}, {"force_tiled": True}, {"force_generic": True}):
+            got, _ = gpu_chain(gpu_ctx, f, dim, t, **kw)
+            assert_same(got, want, t, dim, f"subnormal ties {kw}")
+
+
 def test_golden_fixtures_on_gpu(gpu_ctx, oracle_mod):
     with open(os.path.join(GOLDEN, "golden.json")) as f:
         cases = json.load(f)

@@ -177,6 +177,18 @@ def test_adversarial_half_and_float(ref_mod, oracle_mod):
         assert np.array_equal(a, b), hex(t)
 
 
+def test_subnormal_ties_in_the_reference(ref_mod, oracle_mod):
+    """(b - a) * 0.5 as an inexact subnormal: product and sum are rounded separately (a = 2^-149, b = 2^-148 -> 2^-149)"""
+    out = rchain(ref_mod, np.array([1, 2, 1, 2], np.uint32), (2, 2), T.IMAGE_2D | T.R32F).view(np.uint32)[4]
+    assert out == 1
+    rng = np.random.default_rng(12)
+    small = np.array([0, 1, 2, 3, 4, 5, 6, 7, 9, 11, 0x80000001, 0x80000002, 0x80000003, 0x80000005, 0x00800000, 0x00800001, 0x007FFFFF], np.uint32)
+    for base, fmt, dim in [(T.IMAGE_2D, T.RGBA32F, (64, 64)), (T.IMAGE_3D, T.R32F, (16, 16, 16)), (T.IMAGE_2D, T.RG32F, (50, 30))]:
+        t = base | fmt | M
+        f = small[rng.integers(0, small.size, size=int(np.prod(dim)) * it.channel_count(t))]
+        assert np.array_equal(oracle_mod.generate_mip_map_chain(f, dim, t), ref_mod.generate_mip_map_chain(f, dim, t)), hex(t)
+
+
 def test_timing_build_computes_the_same_bytes(ref_mod, oracle_mod):
     """bench.py's reference arm times the -O3 -march=corei7-avx -mf16c build of the reference (hardware half conversions);
     it must produce what the strict build produces"""
