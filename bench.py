@@ -37,7 +37,7 @@ WORKLOADS = {
     "c3": ("C3: 2D array 2048 layers x 1024^2 RGBA8 UNORM, layers sharded across GPUs", (1024, 1024, 2048), T.IMAGE_2D_ARRAY | T.RGBA8 | M, True, 3),
     "c4": ("C4: cube array 64 x 6 x 4096^2 RGBA32F, cubes sharded across GPUs", (4096, 4096, 64), T.IMAGE_CUBE_ARRAY | T.RGBA32F | M, True, 4),
     "c5": ("C5: 3D volume 512^3 R32F, 2x2x2 minification", (512, 512, 512), T.IMAGE_3D | T.R32F | M, False, 5),
-    # not BASELINE configs: non-power-of-two images take the general (one launch per level) path
+    # not BASELINE configs: non-power-of-two images take the multi-level tile kernel (flmip_tile2d / 3d)
     "n1": ("N1: 3840x2160 RGBA8 UNORM 2D full mip chain (NPOT)", (3840, 2160), T.IMAGE_2D | T.RGBA8 | M, False, 6),
     "n2": ("N2: 2D array 64 layers x 1920x1080 RGBA16F (NPOT)", (1920, 1080, 64), T.IMAGE_2D_ARRAY | T.RGBA16F | M, False, 7),
 }
@@ -262,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "independent images per GPU, no collective" if not sharded else "contiguous layer ranges per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src,
-                         "kernel": ("flmip_fast%dd_*" % (3 if args.workload == "c5" else 2)) if plan["single_pass"] else "flmip_generic", "algorithmic_bytes_per_launch": alg_bytes},
+                         "kernel": ("flmip_fast%dd_*" if plan["single_pass"] else "flmip_tile%dd_*") % (3 if (t >> 16) & 3 == 3 else 2), "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": None if not e2e_steps else {"value": round(total_bytes / (e2e_all * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(e2e_all, 4), "steps": e2e_steps, "blocking_value": round(alg_bytes / (e2e_blocking_ms * 1e-3) / 1e9, 3), "blocking_ms_per_step": round(e2e_blocking_ms, 4),
                     "note": "per step: pinned host level 0 -> H2D -> chain -> D2H of all generated levels; value = non-blocking calls, one queue per image, so the read-back of step k overlaps the upload of step k+1; blocking_value = the reference's blocking semantics on one queue (this rank)"},
