@@ -4,17 +4,19 @@
 TEST INFRASTRUCTURE ONLY (the checker of the checker): it pins oracle/minify_oracle.c, the C restatement, against the
 arithmetic of the reference's own sources.  Nothing of the product path may load it.
 
-What is compiled: `fl::host_device_image<...>::read_linear / write` (include/floor/device/backend/host_image.hpp), the
-vector / const_math / soft_f16 / image_types headers they pull in (16 headers, see NEEDED) and the five-line kernel body of
-include/floor/device/backend/mip_map_minify.hpp:78-108 replayed by oracle/ref_harness.cpp (ours) in the level / layer loop of
+What is compiled: all 17 kernels `libfloor_mip_map_minify_<IMAGE>_<SAMPLE>` of include/floor/device/backend/mip_map_minify.hpp,
+`fl::image<>::read_lod_linear / write_lod` (image.hpp), `fl::host_device_image<...>::read_linear / write`
+(host_image.hpp), the vector / const_math / soft_f16 / image_types headers they pull in (see NEEDED) and the reference's own
+explicit vector instantiations (REF_SOURCES); oracle/ref_harness.cpp (ours) drives the kernels in the level / layer loop of
 src/device/device_image.cpp:290-327.
 
 libfloor only supports clang >= 19 (include/floor/floor_version.hpp:96-129) and these headers use clang-only extensions that
 g++ 13 cannot parse.  The headers are therefore read where they lie under /root/reference, a SMALL LIST OF MECHANICAL,
 arithmetic-neutral substitutions (PATCHES below; each one says what and why) is applied in a temporary directory, and only
 the resulting shared object is kept, in oracle/_ref/ (git-ignored).  No reference source is copied into the repository.
-None of the substitutions touches a line that computes a texel: coordinate handling, texel fetch, format decode, the lerp
-(`const_math::interpolate`), format encode and the level-size math are the reference's own code, compiled as strict IEEE
+None of the substitutions changes what a line computes: coordinate handling, texel fetch, format decode, the lerp
+(`const_math::interpolate`), format encode and the level-size math are the reference's own code (the 1D sampler and the depth
+read get an implicit vector1 -> scalar conversion spelled out, nothing else on the texel path is touched), compiled as strict IEEE
 (-fno-fast-math -ffp-contract=off), which is the canonical numeric mode of SURVEY.md 8c.
 
 /root/reference does not exist on the GPU box: the .so is built here (by __graft_entry__.build()) and travels with the repo
@@ -111,12 +113,17 @@ PATCHES = [
      "\t\telse { return rt_func (ARG_EXPANDER(, FLOOR_COMMA)); } \\\n"
      "\t}\n\t\n#define FLOOR_CONST_SELECT_1",
      1, "const-select macro: is_constant_evaluated() instead of enable_if/asm-label overloads"),
-    # g++ rejects clang's implicit vector1 <-> scalar conversions that only the 1D sampler (host_image.hpp:859-865) and the
-    # 1-channel depth read (image.hpp:519) rely on: those two kernel families are not instantiated.
-    ("floor/device/backend/mip_map_minify.hpp", r"F\(kernel_1d, IMAGE_1D(?:_ARRAY)?, (?:FLOAT|INT|UINT)\) \\\n", "", 6,
-     "1D / 1D-array kernels are not instantiated"),
-    ("floor/device/backend/mip_map_minify.hpp", r"^FLOOR_MINIFY_DEPTH_IMAGE_TYPES\(F\)\n", "\n", 1,
-     "depth kernels are not instantiated"),
+    # clang converts vector1<T> <-> T implicitly where g++ sees an ambiguity (vector1's own operator< through the converting
+    # constructor vs the built-in one through the conversion operator; fit(T) vs fit(vector4<T>)).  The 1D sampler
+    # (host_image.hpp:859-865) and the 1-channel depth read (image.hpp:519) get the conversion spelled out: same value.
+    ("floor/device/backend/host_image.hpp", r"\(frac_coord < 0\.5f \? frac_coord \+ 0\.5f : 1\.5f - frac_coord\)",
+     "(frac_coord.x < 0.5f ? frac_coord.x + 0.5f : 1.5f - frac_coord.x)", 2,
+     "1D read_linear / compare_linear: the weight as an explicit scalar (frac_coord is a vector1<float>)"),
+    ("floor/device/backend/host_image.hpp", r"frac_coord < 0\.5f", "frac_coord.x < 0.5f", 2,
+     "1D read_linear / compare_linear: explicit vector1<float> -> float in the neighbour-offset comparison"),
+    ("floor/device/backend/image.hpp", r"(#else\n\t+)return output_type::fit\(color\);",
+     r"\1if constexpr (std::is_same_v<std::decay_t<decltype(color)>, vector1<sample_type>>) { return output_type::fit(color.x); } else { return output_type::fit(color); }",
+     1, "depth read: explicit vector1<float> -> float before image_vec_ret_type::fit"),
     # FLOOR_DEVICE_NO_DOUBLE (device-run Host-Compute builds: all-float encoder scale, host_image.hpp:398-402) cannot be
     # defined for the whole host-mode header set (vector_helper.hpp:983 drops double while vector_lib.hpp:85-100 still lists
     # it), so the one #if on the path gets its own switch; the second build defines it.

@@ -8,9 +8,9 @@
  * compile with g++ through oracle/build_ref.py (-> oracle/_ref/); tests/test_reference_pin.py
  * requires this restatement to equal them bit for bit (all formats, 2D / array / cube / 3D,
  * POT and NPOT, both encoder-scale modes, adversarial floats, BASELINE configs), and
- * tests/golden/golden_ref.json freezes reference-computed chains.  1D and depth images are the
- * exception (their reference kernels do not compile with g++): pinned by source semantics and
- * the numpy emulation only.  Evaluated in strict IEEE-754 order (-fno-fast-math -ffp-contract=off).
+ * tests/golden/golden_ref.json freezes reference-computed chains.  All 17 kernels of
+ * FLOOR_MINIFY_IMAGE_TYPES (1D, 1D-array, 2D, 2D-array, 3D x FLOAT / INT / UINT, depth, depth-array)
+ * are covered.  Evaluated in strict IEEE-754 order (-fno-fast-math -ffp-contract=off).
  *
  * Each function cites the reference file:line (relative to a2flo/floor) it follows:
  *   kernel ................. include/floor/device/backend/mip_map_minify.hpp:78-108

@@ -15,8 +15,8 @@
 //   * kernel selection by `minify_image_base_type` (mip_map_minify.hpp:53-69, device_image.cpp:255-287); cube images
 //     have no kernel in the reference (static_assert :95-97), they run here as the 2D array of 6N layers they are
 //     stored as (host_image.hpp:263-271) -- the same decision the oracle documents.
-// 1D and depth kernels are not instantiated: g++ rejects clang's implicit vector1 <-> scalar conversions in
-// host_image.hpp:859-865 / image.hpp:519; those two families stay pinned by the restatement's own tests only.
+// All 17 kernels of FLOOR_MINIFY_IMAGE_TYPES are instantiated (1D, 1D-array, 2D, 2D-array, 3D x FLOAT / INT / UINT + the two
+// depth kernels).
 //
 // Only tests/ may load the resulting oracle/_ref/libfloor_ref_minify*.so.
 #include <cstdint>
@@ -150,8 +150,24 @@ void launch(kernel_fn<kernel_image_type> fn, program_info_t* info, const fl::uin
 		return true; \
 	}
 
+// depth kernels carry no CHANNELS_4 (mip_map_minify.hpp:113-115); their key keeps the channel bits (:64-67)
+#define REF_CASE_DEPTH(image_type) \
+	if (base == (IMAGE_TYPE::image_type | IMAGE_TYPE::FLOAT)) { \
+		launch<(IMAGE_TYPE::image_type | IMAGE_TYPE::FLOAT)>(&libfloor_mip_map_minify_##image_type##_FLOAT, info, level_size, inv_prev, level, layer, \
+															 dim_count, threads); \
+		return true; \
+	}
+
 bool dispatch(IMAGE_TYPE base, program_info_t* info, const fl::uint3& level_size, const fl::float3& inv_prev, uint32_t level,
 			  uint32_t layer, uint32_t dim_count, uint32_t threads) {
+	REF_CASE(IMAGE_1D, FLOAT)
+	REF_CASE(IMAGE_1D, INT)
+	REF_CASE(IMAGE_1D, UINT)
+	REF_CASE(IMAGE_1D_ARRAY, FLOAT)
+	REF_CASE(IMAGE_1D_ARRAY, INT)
+	REF_CASE(IMAGE_1D_ARRAY, UINT)
+	REF_CASE_DEPTH(IMAGE_DEPTH)
+	REF_CASE_DEPTH(IMAGE_DEPTH_ARRAY)
 	REF_CASE(IMAGE_2D, FLOAT)
 	REF_CASE(IMAGE_2D, INT)
 	REF_CASE(IMAGE_2D, UINT)

@@ -59,6 +59,11 @@ CASES = [
     ("vol_128_rgba8ui", (128, 128, 128), T.IMAGE_3D | T.RGBA8UI, 31, False, 0, False),
     ("array_2x512_rgba16i_norm", (512, 512, 2), T.IMAGE_2D_ARRAY | T.RGBA16I_NORM, 32, False, 0, False),
     ("rgb8_200x120", (200, 120), T.IMAGE_2D | T.RGB8, 33, False, 0, False),
+    ("1d_1000_rgba8", (1000,), T.IMAGE_1D | T.RGBA8, 24, False, 0, False),
+    ("1darray_256x3_r32f", (256, 3), T.IMAGE_1D_ARRAY | T.R32F, 25, False, 0, False),
+    ("depth_256_d32f", (256, 256), T.D32F, 27, False, 0, False),
+    ("deptharray_100x60x2_d32f", (100, 60, 2), T.IMAGE_DEPTH_ARRAY | T.FORMAT_32 | T.FLOAT, 34, False, 0, False),
+    ("quirk_2624x188_rgba8", (2624, 188), T.IMAGE_2D | T.RGBA8, 35, False, 0, False),
     # BASELINE.json configs at full size (config ids as in bench.py)
     ("C2_8192_rgba16f", (8192, 8192), T.IMAGE_2D | T.RGBA16F, 2, False, 0, True),
     ("C3_shard_8x1024_rgba8", (1024, 1024, 8), T.IMAGE_2D_ARRAY | T.RGBA8, 3, False, 0, True),

@@ -116,7 +116,8 @@ SHAPES = [(T.IMAGE_2D, (64, 64)), (T.IMAGE_2D, (20, 12)), (T.IMAGE_2D, (37, 5)),
           (T.IMAGE_2D_ARRAY, (16, 8, 3)), (T.IMAGE_2D_ARRAY, (11, 23, 2)), (T.IMAGE_3D, (16, 16, 16)), (T.IMAGE_3D, (12, 10, 6)),
           (T.IMAGE_3D, (7, 33, 5)), (T.IMAGE_CUBE, (8, 8)), (T.IMAGE_CUBE_ARRAY, (6, 6, 2)),
           # sizes where the reference's linear fetch for destination texel 0 reads texels 0 and 2 (tests/test_npot_weights.py)
-          (T.IMAGE_2D, (41, 47)), (T.IMAGE_2D, (83, 164)), (T.IMAGE_3D, (55, 61, 41)), (T.IMAGE_2D_ARRAY, (97, 94, 2))]
+          (T.IMAGE_2D, (41, 47)), (T.IMAGE_2D, (83, 164)), (T.IMAGE_3D, (55, 61, 41)), (T.IMAGE_2D_ARRAY, (97, 94, 2)),
+          (T.IMAGE_1D, (33,)), (T.IMAGE_1D, (256,)), (T.IMAGE_1D, (41,)), (T.IMAGE_1D_ARRAY, (64, 2)), (T.IMAGE_1D_ARRAY, (97, 3))]
 
 
 @pytest.mark.parametrize("fmt", FORMATS)
@@ -134,12 +135,24 @@ def test_oracle_matches_reference(ref_mod, oracle_mod, fmt):
             assert np.array_equal(a, b), (hex(t), dim, "no_double")
 
 
+def test_depth_images_match_reference(ref_mod, oracle_mod):
+    """libfloor_mip_map_minify_IMAGE_DEPTH[_ARRAY]_FLOAT (mip_map_minify.hpp:22-30): D32F, single channel"""
+    for dim, t in [((256, 256), T.D32F | M), ((100, 37), T.D32F | M), ((41, 47), T.D32F | M),
+                   ((64, 32, 3), T.IMAGE_DEPTH_ARRAY | T.FORMAT_32 | T.FLOAT | M)]:
+        l0 = oracle_mod.fill_synthetic(dim, t, 27)
+        assert np.array_equal(oracle_mod.generate_mip_map_chain(l0, dim, t), ref_mod.generate_mip_map_chain(l0, dim, t)), (hex(t), dim)
+
+
 def test_random_geometry_fuzz(ref_mod, oracle_mod):
     rng = np.random.default_rng(20261017)
-    for i in range(120):
+    for i in range(160):
         fmt = FORMATS[int(rng.integers(len(FORMATS)))]
-        kind = int(rng.integers(3))
-        if kind == 0:
+        kind = int(rng.integers(5))
+        if kind == 3:
+            base, dim = T.IMAGE_1D, (int(rng.integers(1, 600)),)
+        elif kind == 4:
+            base, dim = T.IMAGE_1D_ARRAY, (int(rng.integers(1, 200)), int(rng.integers(1, 4)))
+        elif kind == 0:
             base, dim = T.IMAGE_2D, tuple(int(x) for x in rng.integers(1, 90, 2))
         elif kind == 1:
             base, dim = T.IMAGE_2D_ARRAY, tuple(int(x) for x in rng.integers(1, 50, 2)) + (int(rng.integers(1, 4)),)
