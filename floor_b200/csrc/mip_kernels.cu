@@ -1229,6 +1229,11 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 		axis_f fix[INV];
 		fix[0] = axis_fetch(min(ti[0] * EX + t % EX, W1 - 1u), P.inv_prev[0][0], P.fdim[0][0], P.fdim_excl[0][0]);
 		if constexpr (D == 3) fix[1] = axis_fetch(min(ti[1] * EY + (t / EX) % EY, H1 - 1u), P.inv_prev[0][1], P.fdim[0][1], P.fdim_excl[0][1]);
+		// 2D: the warp's four rows are fetched once by lanes 0..3 and handed round with shuffles
+		axis_f rowf = { 0.0f, 0u, 0u };
+		if constexpr (D == 2) rowf = axis_fetch(min(ti[1] * EY + warp * PER_THREAD + (lane & 3u), H1 - 1u), P.inv_prev[0][1], P.fdim[0][1], P.fdim_excl[0][1]);
+		const uint64_t pitch = (uint64_t)W0 * BPP;
+		const uint32_t xoff[2] = { fix[0].a * BPP, fix[0].b * BPP };
 #pragma unroll 1
 		for (int c = 0; c < PER_THREAD; c += U) {
 			uint32_t raw[U][1 << D][NW];
@@ -1241,17 +1246,27 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 				const uint32_t ox = o[u] % EX, oy = (o[u] / EX) % EY, oz = o[u] / (EX * EY);
 				g[u][0] = ti[0] * EX + ox; g[u][1] = ti[1] * EY + oy; g[u][2] = (D == 3 ? ti[2] * (G::TZ / 2) + oz : 0u);
 				ok[u] = g[u][0] < W1 && g[u][1] < H1 && (D < 3 || g[u][2] < D1);
+				uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+				wt[u][0] = fix[0].t;
+				if constexpr (D == 2) {
+					wt[u][1] = __shfl_sync(0xFFFFFFFFu, rowf.t, c + u);
+					s[1][0] = __shfl_sync(0xFFFFFFFFu, rowf.a, c + u);
+					s[1][1] = __shfl_sync(0xFFFFFFFFu, rowf.b, c + u);
+				} else {
+					wt[u][1] = fix[1].t; s[1][0] = fix[1].a; s[1][1] = fix[1].b;
+				}
 				if (ok[u]) {
-					uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
-#pragma unroll
-					for (int d = 0; d < D; ++d) {
-						const axis_f f = d < INV ? fix[d < INV ? d : 0] : axis_fetch(g[u][d], P.inv_prev[0][d], P.fdim[0][d], P.fdim_excl[0][d]);
-						wt[u][d] = f.t; s[d][0] = f.a; s[d][1] = f.b;
+					if constexpr (D == 3) {
+						const axis_f f = axis_fetch(g[u][2], P.inv_prev[0][2], P.fdim[0][2], P.fdim_excl[0][2]);
+						wt[u][D - 1] = f.t; s[2][0] = f.a; s[2][1] = f.b;
 					}
 #pragma unroll
-					for (int k = 0; k < (1 << D); ++k) {
-						const uint64_t sx = s[0][k & 1], sy = s[1][(k >> 1) & 1], sz = s[2][(k >> 2) & 1];
-						IO::template load<false>(src + ((sz * H0 + sy) * W0 + sx) * BPP, raw[u][k]);
+					for (int r = 0; r < (1 << (D - 1)); ++r) {
+						// one row pointer per (y, z) choice, two texels (A, B along x) from it
+						const uint64_t row = (D == 3 ? (uint64_t)s[2][(r >> 1) & 1] * H0 : 0ull) + s[1][r & 1];
+						const uint8_t* const rp = src + row * pitch;
+						IO::template load<false>(rp + xoff[0], raw[u][2 * r]);
+						IO::template load<false>(rp + xoff[1], raw[u][2 * r + 1]);
 					}
 				}
 			}
