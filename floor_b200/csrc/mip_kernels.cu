@@ -1433,8 +1433,12 @@ FLMIP_FAST_KERNELS_FOR_KIND(10)
 FLMIP_FAST_KERNELS_FOR_KIND(11)
 #endif
 
+// 2D, texels below 16 bytes: 5 CTAs per SM (48 registers, at most 8 bytes of spills) -- the tile kernel is latency-bound there;
+// measured on N2 (RGBA16F): 4 CTAs 4 818 GB/s, 5 CTAs 5 018 GB/s, 6 CTAs 4 696 GB/s.  3D and 16-byte texels keep ptxas' choice
+// (they would spill 16 .. 200 bytes).
+#define FLMIP_TILE_MIN_BLOCKS(D, K, CHN) (((D) == 2 && flmip_elem_bytes(K) * (CHN) < 16) ? 5 : 1)
 #define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
-	extern "C" __global__ void __launch_bounds__(256) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
+	extern "C" __global__ void __launch_bounds__(256, FLMIP_TILE_MIN_BLOCKS(D, K, CHN)) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
 		tile_body<K, CHN, D>(P);                                                                                                 \
 	}
 #define FLMIP_TILE_KERNELS_FOR_KIND(K) \
