@@ -9,7 +9,7 @@ nproc > $out/nproc.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
 tail -3 $out/pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -1 $out/smoke.log
-for w in c2 c1 c5 c3 c4; do
+for w in c2 c1 c5 c3 c4 n1 n2; do
   timeout 900 python bench.py --workload $w --steps 20 --warmup 5 > $out/bench_$w.json 2> $out/bench_$w.err; cut -c1-400 $out/bench_$w.json
 done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2>&1

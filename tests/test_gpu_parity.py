@@ -327,6 +327,20 @@ def test_relaunch_is_idempotent_and_counters_reset(gpu_ctx, oracle_mod):
     img.destroy()
 
 
+def test_layout_and_srgb_flags_do_not_change_the_arithmetic(gpu_ctx, oracle_mod):
+    """BGRA / ABGR / ARGB layouts and FLAG_SRGB are properties of how a sampler interprets channels; the minify path treats the
+    stored channels alike, so the chains must be byte-identical to plain RGBA"""
+    for dim, base in [((256, 128), T.IMAGE_2D | T.RGBA8), ((100, 60), T.IMAGE_2D | T.RGBA8), ((64, 64, 2), T.IMAGE_2D_ARRAY | T.RGBA16F)]:
+        l0 = oracle_mod.fill_synthetic(dim, base | M, 91)
+        plain, _ = gpu_chain(gpu_ctx, l0, dim, base | M)
+        assert_same(plain, oracle_mod.generate_mip_map_chain(l0, dim, base | M, threads=4), base | M, dim, "rgba")
+        for extra in (T.LAYOUT_BGRA, T.LAYOUT_ABGR, T.LAYOUT_ARGB, T.FLAG_SRGB, T.LAYOUT_BGRA | T.FLAG_SRGB):
+            t = base | extra | M
+            got, _ = gpu_chain(gpu_ctx, l0, dim, t)
+            assert_same(got, plain, t, dim, "layout / srgb variant")
+            assert_same(oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4), plain, t, dim, "oracle, layout / srgb variant")
+
+
 def test_unsupported_types_are_rejected(gpu_ctx):
     ctx, dev, q = gpu_ctx
     for t, dim in [(T.IMAGE_2D | T.RGB8 | M, (64, 64)), (T.IMAGE_2D | T.FORMAT_64 | T.FLOAT | T.CHANNELS_1 | M, (64, 64)),

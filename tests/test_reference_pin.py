@@ -135,6 +135,17 @@ def test_oracle_matches_reference(ref_mod, oracle_mod, fmt):
             assert np.array_equal(a, b), (hex(t), dim, "no_double")
 
 
+def test_layout_and_srgb_flags_in_the_reference(ref_mod, oracle_mod):
+    """channel layouts (BGRA, ABGR, ARGB) and FLAG_SRGB leave the reference's minify arithmetic untouched"""
+    dim, base = (100, 60), T.IMAGE_2D | T.RGBA8
+    l0 = oracle_mod.fill_synthetic(dim, base | M, 91)
+    plain = ref_mod.generate_mip_map_chain(l0, dim, base | M)
+    for extra in (T.LAYOUT_BGRA, T.LAYOUT_ABGR, T.LAYOUT_ARGB, T.FLAG_SRGB):
+        t = base | extra | M
+        assert np.array_equal(ref_mod.generate_mip_map_chain(l0, dim, t), plain), hex(t)
+        assert np.array_equal(oracle_mod.generate_mip_map_chain(l0, dim, t), plain), hex(t)
+
+
 def test_depth_images_match_reference(ref_mod, oracle_mod):
     """libfloor_mip_map_minify_IMAGE_DEPTH[_ARRAY]_FLOAT (mip_map_minify.hpp:22-30): D32F, single channel"""
     for dim, t in [((256, 256), T.D32F | M), ((100, 37), T.D32F | M), ((41, 47), T.D32F | M),
