@@ -17,5 +17,8 @@ for w in c2 c5 c3; do
   extra=""; [ $w = c3 ] && extra="--layers 256"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/launches_$w.csv python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline $extra > $out/ncu_launch_$w.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:flmip_fast -s 3 -c 1 -f -o $out/prof_$w python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e $extra > $out/ncu_full_$w.log 2>&1
+  # gpurun_out/ is limited to 64 MiB: summarise on the box, keep only the C2 report itself
+  python scripts/ncu_summary.py $out/prof_$w.ncu-rep > $out/ncu_full_summary_$w.txt 2>&1
+  [ $w = c2 ] || rm -f $out/prof_$w.ncu-rep
 done
 ls -la $out
