@@ -484,3 +484,43 @@ def test_tiled_interop_round_trip(gpu_ctx, oracle_mod, base, dim, fmt):
     assert_same(got, want, t, dim, "tiled array contents")
     img.destroy_tiled(arr)
     img.destroy()
+
+
+def test_concurrent_host_threads_and_all_devices(built_lib, oracle_mod):
+    """the entry points are callable from any thread (each call makes the device's context current on the calling thread, like
+    cuda_function.cpp:83-87), and one context serves every GPU of the box (cuda_context.cpp:80-128): 2 threads per visible
+    device, each with its own queue and images, all running chains at the same time"""
+    import threading
+    ctx = floor_b200.device_context()
+    devs = ctx.get_devices()
+    cases = [((512, 256), T.IMAGE_2D | T.RGBA8 | M), ((300, 200), T.IMAGE_2D | T.RGBA16F | M), ((64, 64, 32), T.IMAGE_3D | T.R32F | M),
+             ((128, 128, 4), T.IMAGE_2D_ARRAY | T.RGBA8 | M)]
+    want = {}
+    for i, (dim, t) in enumerate(cases):
+        l0 = oracle_mod.fill_synthetic(dim, t, 400 + i)
+        want[i] = (l0, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4))
+    errors = []
+
+    def worker(dev, k):
+        try:
+            q = ctx.create_queue(dev)
+            for rep in range(6):
+                i = (k + rep) % len(cases)
+                dim, t = cases[i]
+                img = ctx.create_image(q, dim, t)
+                img.upload_levels(q, want[i][0], 0, 0)
+                img.generate_mip_map_chain(q)
+                got = img.download_levels(q)
+                img.destroy()
+                if not np.array_equal(got, want[i][1]):
+                    errors.append((dev.index, k, i))
+            q.destroy()
+        except Exception as e:  # noqa: BLE001
+            errors.append((dev.index, k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(d, k)) for d in devs for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
