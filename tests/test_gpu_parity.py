@@ -96,7 +96,9 @@ def test_tile_kernel_all_formats(gpu_ctx, oracle_mod, fmt):
              (T.IMAGE_3D, (70, 33, 18), {}), (T.IMAGE_3D, (65, 40, 100), {}), (T.IMAGE_2D, (256, 128), {"force_tiled": True}),
              (T.IMAGE_3D, (64, 32, 32), {"force_tiled": True}), (T.IMAGE_2D, (64, 4), {}), (T.IMAGE_2D, (5, 3), {}),
              # texel-2 quirk sizes (tests/test_npot_weights.py) at level 0 and, via 2624 = 41 << 6 / 188 = 47 << 2, deep inside a tile
-             (T.IMAGE_2D, (41, 47), {}), (T.IMAGE_2D, (2624, 188), {}), (T.IMAGE_3D, (55, 61, 41), {}), (T.IMAGE_3D, (328, 94, 82), {})]
+             (T.IMAGE_2D, (41, 47), {}), (T.IMAGE_2D, (2624, 188), {}), (T.IMAGE_3D, (55, 61, 41), {}), (T.IMAGE_3D, (328, 94, 82), {}),
+             # ... and where the host has to cut a launch short: level 5 is 41 wide (a tile holds 2 texels of it), depth 41 at level 3
+             (T.IMAGE_2D, (1312, 200), {}), (T.IMAGE_2D, (96, 1504), {}), (T.IMAGE_3D, (40, 48, 328), {})]
     for base, dim, kw in cases:
         t = base | fmt | M
         l0 = oracle_mod.fill_synthetic(dim, t, 600 + (fmt & 0xFFFF))
@@ -111,7 +113,8 @@ def test_tile_kernel_all_formats(gpu_ctx, oracle_mod, fmt):
 def test_tile_kernel_launch_plan_and_large_npot(gpu_ctx, oracle_mod):
     """3840 x 2160 RGBA8 (12 levels) = 2 launches; 64 layers of 1920 x 1080 RGBA16F; a 300 x 200 x 100 volume"""
     for base, fmt, dim, launches in [(T.IMAGE_2D, T.RGBA8, (3840, 2160), 2), (T.IMAGE_2D_ARRAY, T.RGBA16F, (1920, 1080, 6), 2),
-                                     (T.IMAGE_3D, T.R32F, (300, 200, 100), 2), (T.IMAGE_2D, T.R8, (4097, 33), 1), (T.IMAGE_2D, T.RG8, (5000, 3000), 2)]:
+                                     (T.IMAGE_3D, T.R32F, (300, 200, 100), 2), (T.IMAGE_2D, T.R8, (4097, 33), 1), (T.IMAGE_2D, T.RG8, (5000, 3000), 2),
+                                     (T.IMAGE_2D, T.RGBA8, (1312, 1312), 2)]:
         t = base | fmt | M
         l0 = oracle_mod.fill_synthetic(dim, t, 77)
         got, plan = gpu_chain(gpu_ctx, l0, dim, t)
