@@ -34,3 +34,14 @@ def test_dropin_parity_on_gpu(built_lib, oracle_mod):
     res = subprocess.run([exe, oracle_so], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "dropin_test: ok" in res.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_bench_program_runs(built_lib):
+    """tests/cpp/mipbench.cpp: the C++ host API (cuda_context -> queue -> image -> generate_mip_map_chain) timed with the queue's own
+    profiling; a 8192^2 RGBA16F chain has to stay far above anything a CPU path could do (no silent fallback)"""
+    subprocess.check_call(["make", "-s", "-C", CPP, "mipbench"])
+    res = subprocess.run([os.path.join(CPP, "mipbench"), "c2", "10"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stdout + res.stderr
+    gbs = float(res.stdout.split("enqueued")[1].split("=")[1].split("GB/s")[0])
+    assert gbs > 1000.0, res.stdout
