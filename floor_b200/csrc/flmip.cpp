@@ -51,7 +51,7 @@ int fail(int code, const char* fmt, ...) {
 	F(cuCtxPopCurrent) F(cuMemAlloc) F(cuMemFree) F(cuMemsetD8Async) F(cuMemsetD32Async) F(cuMemcpyHtoDAsync) F(cuMemcpyDtoHAsync) \
 	F(cuMemcpy3DAsync) F(cuMemHostAlloc) F(cuMemFreeHost) F(cuStreamCreate) F(cuStreamDestroy) F(cuStreamSynchronize)            \
 	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
-	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
+	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuLaunchKernelEx) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
 	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy)
 
 struct driver_api {
@@ -227,10 +227,37 @@ int get_function(device_state* ds, const std::string& name, uint32_t dynamic_sme
 	return FLMIP_OK;
 }
 
-int launch(CUfunction fn, uint64_t grid, uint32_t block, uint32_t smem, CUstream stream, void** args) {
+// `dependent` = programmatic dependent launch: the kernel may become resident while its predecessor in the stream drains (its
+// CTAs run their prologue, then block in griddepcontrol.wait until the predecessor has completed and flushed) -- only for
+// kernels that execute griddepcontrol.wait before their first global access (flmip_fast*, flmip_tile*).  FLMIP_PDL=0 disables it.
+bool pdl_enabled() {
+	static const bool on = [] {
+		const char* v = getenv("FLMIP_PDL");
+		return !(v && v[0] == '0');
+	}();
+	return on;
+}
+
+int launch(CUfunction fn, uint64_t grid, uint32_t block, uint32_t smem, CUstream stream, void** args, bool dependent = false) {
 	if (grid == 0) return FLMIP_OK;
 	if (grid > 0x7FFFFFFFull) return fail(FLMIP_ERR_INVALID, "grid of %llu blocks exceeds the launch limit", (unsigned long long)grid);
-	CU_TRY(cu.p_cuLaunchKernel(fn, (unsigned)grid, 1, 1, block, 1, 1, smem, stream, args, nullptr), "cuLaunchKernel");
+	if (dependent && pdl_enabled()) {
+		CUlaunchAttribute attr;
+		memset(&attr, 0, sizeof(attr));
+		attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+		attr.value.programmaticStreamSerializationAllowed = 1;
+		CUlaunchConfig cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.gridDimX = (unsigned)grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+		cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+		cfg.sharedMemBytes = smem;
+		cfg.hStream = stream;
+		cfg.attrs = &attr;
+		cfg.numAttrs = 1;
+		CU_TRY(cu.p_cuLaunchKernelEx(&cfg, fn, args, nullptr), "cuLaunchKernelEx");
+	} else {
+		CU_TRY(cu.p_cuLaunchKernel(fn, (unsigned)grid, 1, 1, block, 1, 1, smem, stream, args, nullptr), "cuLaunchKernel");
+	}
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
 	return FLMIP_OK;
 }
@@ -572,7 +599,7 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 			for (uint32_t d = 0; d < im.dc; ++d)
 				if (axis_reads_texel_2(im.levels[s + k - 1u].dim[d])) T.block_sync = 1u;
 		void* args[] = { &T };
-		const int rc = launch(fn, (uint64_t)T.tiles[0] * T.tiles[1] * T.tiles[2] * im.layers, 256, 0, stream, args);
+		const int rc = launch(fn, (uint64_t)T.tiles[0] * T.tiles[1] * T.tiles[2] * im.layers, 256, 0, stream, args, true);
 		if (rc != FLMIP_OK) return rc;
 	}
 	return FLMIP_OK;
@@ -1012,7 +1039,7 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 		if (rc != FLMIP_OK) return rc;
 		const flmip_fast_params& P = img->fast_params;
 		void* args[] = { &img->tmap, const_cast<flmip_fast_params*>(&P) };
-		rc = launch(fn, img->fast_grid, FLMIP_BLOCK_THREADS, img->fast_smem, (CUstream)stream, args);
+		rc = launch(fn, img->fast_grid, FLMIP_BLOCK_THREADS, img->fast_smem, (CUstream)stream, args, true);
 		if (rc != FLMIP_OK) return rc;
 		next = img->fast_level_count;
 	}

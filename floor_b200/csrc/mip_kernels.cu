@@ -470,6 +470,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 				 : "memory");
 }
 
+// programmatic dependent launch (the host launches flmip_fast* / flmip_tile* with the stream-serialization attribute): everything
+// before pdl_wait() may overlap the tail of the previous kernel in the stream; nothing in global memory may be touched before it.
+// The dependents are released right after, so that at most one successor is ever pending.  No-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait_then_release() {
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -723,6 +731,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		fence_mbar_init();
 	}
 	__syncthreads();
+	pdl_wait_then_release();
 
 	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
 	// the finisher pool is idle when the consumers' in-register levels end the chain
@@ -1214,6 +1223,7 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 	if constexpr (D == 3) { ti[2] = tile % P.tiles[2]; tile /= P.tiles[2]; }
 	const uint32_t layer = tile;
 	uint8_t* const base = reinterpret_cast<uint8_t*>(P.base);
+	pdl_wait_then_release();
 
 	// ---- level 1: straight from global memory (each warp reads whole 2 * BPP * 32 byte row segments) -------------
 	// 2D: warp w owns rows 4w .. 4w+3 of level 1 (so that levels 2 and 3 stay inside the warp); 3D: o = t + c * 256

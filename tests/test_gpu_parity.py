@@ -527,3 +527,29 @@ def test_concurrent_host_threads_and_all_devices(built_lib, oracle_mod):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_back_to_back_chains_on_one_queue(gpu_ctx, oracle_mod):
+    """stream-ordered chains without host waits in between: the single-pass and tile kernels are launched as programmatic dependents
+    (their prologue may overlap the previous kernel's tail, griddepcontrol.wait guards every global access), the literal kernel
+    and the fill kernel are not.  Mixed sequence on one queue, same image relaunched in between, results checked at the end."""
+    ctx, dev, q = gpu_ctx
+    specs = [((512, 512), T.IMAGE_2D | T.RGBA8 | M, {}), ((300, 200), T.IMAGE_2D | T.RGBA16F | M, {}), ((64, 64, 64), T.IMAGE_3D | T.R32F | M, {}),
+             ((33,), T.IMAGE_1D | T.RGBA8 | M, {}), ((128, 128, 3), T.IMAGE_2D_ARRAY | T.RG16 | M, {"force_generic": True}),
+             ((2048, 1024), T.IMAGE_2D | T.RGBA16F | M, {})]
+    imgs, want = [], []
+    for i, (dim, t, kw) in enumerate(specs):
+        l0 = oracle_mod.fill_synthetic(dim, t, 700 + i)
+        im = ctx.create_image(q, dim, t, **kw)
+        im.upload_levels(q, l0, 0, 0)
+        imgs.append(im)
+        want.append(oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4))
+    order = [0, 1, 2, 3, 4, 5, 5, 5, 0, 0, 2, 1, 1, 4, 3, 5, 0, 2] * 6
+    for i in order:
+        imgs[i].enqueue_mip_map_chain(q)
+    imgs[2].fill_synthetic(q, 702)      # a plain kernel in between, rewriting level 0 with the same pattern
+    imgs[2].enqueue_mip_map_chain(q)
+    q.finish()
+    for im, w, (dim, t, kw) in zip(imgs, want, specs):
+        assert_same(im.download_levels(q), w, t, dim, "back-to-back chains")
+        im.destroy()
