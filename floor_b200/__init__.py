@@ -33,6 +33,7 @@ EXPORTS = [
     "flmip_mip_chain_generate", "flmip_mip_chain_generate_from", "flmip_image_fill_synthetic",
     "flmip_image_blit", "flmip_image_create_tiled_twin", "flmip_tiled_destroy", "flmip_image_copy_to_tiled",
     "flmip_image_copy_from_tiled", "flmip_tiled_download", "flmip_device_cu_context",
+    "flmip_batch_create", "flmip_batch_generate", "flmip_batch_kernel_count", "flmip_batch_destroy",
 ]
 
 
@@ -119,6 +120,10 @@ def lib() -> ctypes.CDLL:
         "flmip_image_copy_from_tiled": (i32, [vp, vp, u32, u32, vp]),
         "flmip_tiled_download": (i32, [vp, vp, vp, ctypes.c_size_t, u32, u32, vp]),
         "flmip_device_cu_context": (i32, [i32, ctypes.POINTER(vp)]),
+        "flmip_batch_create": (i32, [ctypes.POINTER(vp), u32, ctypes.POINTER(vp)]),
+        "flmip_batch_generate": (i32, [vp, vp]),
+        "flmip_batch_kernel_count": (i32, [vp, ctypes.POINTER(u32)]),
+        "flmip_batch_destroy": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

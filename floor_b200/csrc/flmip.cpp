@@ -52,7 +52,8 @@ int fail(int code, const char* fmt, ...) {
 	F(cuMemcpy3DAsync) F(cuMemHostAlloc) F(cuMemFreeHost) F(cuStreamCreate) F(cuStreamDestroy) F(cuStreamSynchronize)            \
 	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
 	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuLaunchKernelEx) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
-	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy)
+	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy) F(cuGraphCreate) F(cuGraphAddKernelNode)           \
+	F(cuGraphInstantiate) F(cuGraphLaunch) F(cuGraphExecDestroy) F(cuGraphDestroy)
 
 struct driver_api {
 #define FL_DECL(name) decltype(&name) p_##name = nullptr;
@@ -238,9 +239,35 @@ bool pdl_enabled() {
 	return on;
 }
 
+// While a batch is being built (flmip_batch_create) the launches of the calling thread are recorded as kernel nodes of a CUDA
+// graph instead of being issued: the nodes of one image form a chain, the chains of different images have no edges between them.
+struct graph_recorder {
+	CUgraph graph = nullptr;
+	CUgraphNode last = nullptr; // previous node of the image being recorded
+	bool has_last = false;
+	uint32_t nodes = 0;
+};
+thread_local graph_recorder* tl_recorder = nullptr;
+
 int launch(CUfunction fn, uint64_t grid, uint32_t block, uint32_t smem, CUstream stream, void** args, bool dependent = false) {
 	if (grid == 0) return FLMIP_OK;
 	if (grid > 0x7FFFFFFFull) return fail(FLMIP_ERR_INVALID, "grid of %llu blocks exceeds the launch limit", (unsigned long long)grid);
+	if (tl_recorder) {
+		CUDA_KERNEL_NODE_PARAMS np;
+		memset(&np, 0, sizeof(np));
+		np.func = fn;
+		np.gridDimX = (unsigned)grid; np.gridDimY = 1; np.gridDimZ = 1;
+		np.blockDimX = block; np.blockDimY = 1; np.blockDimZ = 1;
+		np.sharedMemBytes = smem;
+		np.kernelParams = args; // copied by the driver now
+		CUgraphNode node = nullptr;
+		CU_TRY(cu.p_cuGraphAddKernelNode(&node, tl_recorder->graph, tl_recorder->has_last ? &tl_recorder->last : nullptr, tl_recorder->has_last ? 1 : 0, &np),
+			   "cuGraphAddKernelNode");
+		tl_recorder->last = node;
+		tl_recorder->has_last = true;
+		++tl_recorder->nodes;
+		return FLMIP_OK;
+	}
 	if (dependent && pdl_enabled()) {
 		CUlaunchAttribute attr;
 		memset(&attr, 0, sizeof(attr));
@@ -1054,6 +1081,79 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 }
 
 int flmip_mip_chain_generate(flmip_image img, flmip_stream stream) { return flmip_mip_chain_generate_from(img, 0, stream); }
+
+// -- batches of independent textures: the reference loops generate_mip_map_chain over them, one blocking launch per
+//    (image, layer, level).  A batch is a CUDA graph with one chain of kernel nodes per image and no edges between images, so
+//    one cuGraphLaunch replaces N launches (small textures are launch-rate bound: ~6 us of host time per launch) and the GPU
+//    runs the chains of different images concurrently.
+struct flmip_batch_s {
+	int device = 0;
+	CUgraph graph = nullptr;
+	CUgraphExec exec = nullptr;
+	uint32_t nodes = 0, images = 0;
+};
+
+int flmip_batch_create(const flmip_image* images, uint32_t count, flmip_batch* out) {
+	if (!images || !out || count == 0) return fail(FLMIP_ERR_INVALID, "empty batch");
+	*out = nullptr;
+	for (uint32_t i = 0; i < count; ++i) {
+		if (check_image(images[i])) return FLMIP_ERR_INVALID;
+		if (images[i]->device != images[0]->device) return fail(FLMIP_ERR_INVALID, "batch: images live on different devices");
+		for (uint32_t j = 0; j < i; ++j)
+			if (images[j] == images[i]) return fail(FLMIP_ERR_INVALID, "batch: image %u appears twice (its chains would race)", i);
+	}
+	WITH_DEVICE(images[0]->device)
+	graph_recorder rec;
+	CU_TRY(cu.p_cuGraphCreate(&rec.graph, 0), "cuGraphCreate");
+	int rc = FLMIP_OK;
+	tl_recorder = &rec;
+	for (uint32_t i = 0; i < count && rc == FLMIP_OK; ++i) {
+		rec.has_last = false;
+		rc = flmip_mip_chain_generate_from(images[i], 0, nullptr);
+	}
+	tl_recorder = nullptr;
+	CUgraphExec exec = nullptr;
+	if (rc == FLMIP_OK && rec.nodes != 0) {
+		const CUresult r = cu.p_cuGraphInstantiate(&exec, rec.graph, 0);
+		if (r != CUDA_SUCCESS) rc = cu_fail(r, "cuGraphInstantiate");
+	}
+	if (rc != FLMIP_OK) {
+		cu.p_cuGraphDestroy(rec.graph);
+		return rc;
+	}
+	auto* b = new flmip_batch_s;
+	b->device = images[0]->device;
+	b->graph = rec.graph;
+	b->exec = exec;
+	b->nodes = rec.nodes;
+	b->images = count;
+	*out = b;
+	return FLMIP_OK;
+}
+
+int flmip_batch_generate(flmip_batch batch, flmip_stream stream) {
+	if (!batch) return fail(FLMIP_ERR_INVALID, "null batch handle");
+	if (!batch->exec) return FLMIP_OK; // nothing to generate (single-level images)
+	WITH_DEVICE(batch->device)
+	CU_TRY(cu.p_cuGraphLaunch(batch->exec, (CUstream)stream), "cuGraphLaunch");
+	launch_counter.fetch_add(batch->nodes, std::memory_order_relaxed);
+	return FLMIP_OK;
+}
+
+int flmip_batch_kernel_count(flmip_batch batch, uint32_t* out) {
+	if (!batch || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = batch->nodes;
+	return FLMIP_OK;
+}
+
+int flmip_batch_destroy(flmip_batch batch) {
+	if (!batch) return FLMIP_OK;
+	WITH_DEVICE(batch->device)
+	if (batch->exec) cu.p_cuGraphExecDestroy(batch->exec);
+	if (batch->graph) cu.p_cuGraphDestroy(batch->graph);
+	delete batch;
+	return FLMIP_OK;
+}
 
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {
 	if (check_image(img)) return FLMIP_ERR_INVALID;

@@ -366,6 +366,41 @@ class device_image:
             pass
 
 
+class mip_chain_batch:
+    """Batch of independent textures: one CUDA graph with a chain of kernel nodes per image and no edges between
+    images, so `generate` is one graph launch and the chains run concurrently.  No equivalent in the reference, which loops
+    generate_mip_map_chain over the images (one blocking launch per image, layer and level).  Destroy before the images."""
+
+    def __init__(self, images):
+        self.images = list(images)
+        self.dev = self.images[0].dev
+        arr = (ctypes.c_void_p * len(self.images))(*[im._handle for im in self.images])
+        self._handle = ctypes.c_void_p()
+        _check(_L().flmip_batch_create(arr, len(self.images), ctypes.byref(self._handle)))
+        n = ctypes.c_uint32()
+        _check(_L().flmip_batch_kernel_count(self._handle, ctypes.byref(n)))
+        self.kernel_count = n.value
+
+    def enqueue(self, cqueue: device_queue):
+        _check(_L().flmip_batch_generate(self._handle, cqueue._stream))
+
+    def generate(self, cqueue: device_queue):
+        """blocking, like generate_mip_map_chain"""
+        self.enqueue(cqueue)
+        cqueue.finish()
+
+    def destroy(self):
+        if self._handle:
+            _L().flmip_batch_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class device_context:
     """cuda_context subset (include/floor/device/cuda/cuda_context.hpp:40-41): constructible without floor::init"""
 
@@ -398,3 +433,6 @@ class device_context:
     def create_image(self, cqueue: device_queue, image_dim, image_type: int, data=None,
                      flags: int = MEMORY_FLAG.HOST_READ_WRITE, mip_level_limit: int = 0, **kw) -> device_image:
         return device_image(cqueue, image_dim, image_type, data, flags, mip_level_limit, **kw)
+
+    def create_mip_chain_batch(self, images) -> mip_chain_batch:
+        return mip_chain_batch(images)

@@ -412,6 +412,40 @@ protected:
 };
 using cuda_image = device_image;
 
+//! Batch of independent textures: one CUDA graph with a chain of kernel nodes per image and no edges between images;
+//! generate() is one graph launch, the chains of the images run concurrently.  No equivalent in the reference, which loops
+//! generate_mip_map_chain over the images.  Must not outlive its images.
+class mip_chain_batch {
+public:
+	explicit mip_chain_batch(std::span<device_image* const> images) {
+		std::vector<flmip_image> handles;
+		for (auto* img : images) handles.push_back(img ? img->get_native_handle() : nullptr);
+		if (flmip_batch_create(handles.data(), uint32_t(handles.size()), &handle) != FLMIP_OK) {
+			FLB_LOG_ERROR("failed to create mip chain batch: %s", flmip_last_error_string());
+			handle = nullptr;
+		}
+	}
+	~mip_chain_batch() {
+		if (handle) flmip_batch_destroy(handle);
+	}
+	mip_chain_batch(const mip_chain_batch&) = delete;
+	mip_chain_batch& operator=(const mip_chain_batch&) = delete;
+	bool is_valid() const { return handle != nullptr; }
+	//! enqueue only
+	bool generate_async(const device_queue& cqueue) const {
+		return handle && flmip_batch_generate(handle, const_cast<void*>(cqueue.get_queue_ptr())) == FLMIP_OK;
+	}
+	//! blocking, like device_image::generate_mip_map_chain
+	bool generate(const device_queue& cqueue) const {
+		if (!generate_async(cqueue)) return false;
+		cqueue.finish();
+		return true;
+	}
+
+protected:
+	flmip_batch handle { nullptr };
+};
+
 //! device_context / cuda_context: constructible without floor::init (cuda_context.hpp:40-41)
 class device_context {
 public:

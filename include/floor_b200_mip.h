@@ -36,6 +36,7 @@ extern "C" {
 #define FLMIP_IMAGE_FORCE_TILED 16u  /* never use the persistent single-pass kernel: multi-level tile kernel for every level (validation / A-B timing) */
 
 typedef struct flmip_image_s* flmip_image;
+typedef struct flmip_batch_s* flmip_batch;
 typedef void* flmip_stream; /* CUstream */
 typedef void* flmip_event;  /* CUevent */
 
@@ -128,6 +129,15 @@ int flmip_device_cu_context(int device, void** out);
 int flmip_mip_chain_generate(flmip_image img, flmip_stream stream);
 /* regenerate only levels > first_level (dirty-level update); first_level = 0 is the full chain */
 int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream);
+
+/* -- batches of independent textures (the reference loops generate_mip_map_chain over them, device_image.cpp:304-327
+ *    per image): one CUDA graph with a chain of kernel nodes per image and no edges between images.  flmip_batch_generate is
+ *    ONE graph launch on `stream`; the chains of the images run concurrently.  All images on one device, each at most once;
+ *    destroy the batch before any of its images. */
+int flmip_batch_create(const flmip_image* images, uint32_t count, flmip_batch* out);
+int flmip_batch_generate(flmip_batch batch, flmip_stream stream);
+int flmip_batch_kernel_count(flmip_batch batch, uint32_t* out); /* kernel nodes one flmip_batch_generate runs */
+int flmip_batch_destroy(flmip_batch batch);
 
 /* -- bench / validation helper: fill level 0 with the counter-based synthetic pattern of SURVEY.md 8d
  *    (the CPU checker defines the same pattern); global layer ids start at layer_id0 */

@@ -553,3 +553,32 @@ def test_back_to_back_chains_on_one_queue(gpu_ctx, oracle_mod):
     for im, w, (dim, t, kw) in zip(imgs, want, specs):
         assert_same(im.download_levels(q), w, t, dim, "back-to-back chains")
         im.destroy()
+
+
+def test_batch_of_independent_textures(gpu_ctx, oracle_mod):
+    """flmip_batch_*: one CUDA graph launch generates the chains of many independent textures (different sizes, formats and kernels:
+    single-pass, tile with two launches, literal 1D); relaunching the batch after rewriting level 0 regenerates them"""
+    ctx, dev, q = gpu_ctx
+    specs = [((1024, 1024), T.IMAGE_2D | T.RGBA8 | M), ((512, 256), T.IMAGE_2D | T.RGBA16F | M), ((300, 200), T.IMAGE_2D | T.RGBA8 | M),
+             ((3840, 2160), T.IMAGE_2D | T.RGBA8 | M), ((64, 64, 64), T.IMAGE_3D | T.R32F | M), ((70, 33, 18), T.IMAGE_3D | T.RG16 | M),
+             ((33,), T.IMAGE_1D | T.RGBA8 | M), ((256, 256, 3), T.IMAGE_2D_ARRAY | T.RGBA32F | M), ((1, 1), T.IMAGE_2D | T.RGBA8 | M)]
+    specs += [((1024, 1024), T.IMAGE_2D | T.RGBA8 | M)] * 8
+    imgs = [ctx.create_image(q, dim, t) for dim, t in specs]
+    batch = ctx.create_mip_chain_batch(imgs)
+    assert batch.kernel_count >= len(specs) - 1  # the 1 x 1 image has nothing to generate, 1D / NPOT images need several kernels
+    for cid in (800, 900):
+        want = []
+        for i, ((dim, t), im) in enumerate(zip(specs, imgs)):
+            l0 = oracle_mod.fill_synthetic(dim, t, cid + i)
+            im.upload_levels(q, l0, 0, 0, sync=False)
+            want.append(oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4))
+        before = floor_b200.lib().flmip_launch_count()
+        batch.generate(q)
+        assert floor_b200.lib().flmip_launch_count() - before == batch.kernel_count
+        for (dim, t), im, w in zip(specs, imgs, want):
+            assert_same(im.download_levels(q), w, t, dim, "batch")
+    with pytest.raises(floor_b200.FlmipError):
+        ctx.create_mip_chain_batch([imgs[0], imgs[0]])
+    batch.destroy()
+    for im in imgs:
+        im.destroy()
