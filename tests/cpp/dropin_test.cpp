@@ -150,6 +150,39 @@ int main(int argc, char** argv) {
 			}
 		}
 	}
+	// a batch of independent textures: one graph launch, every chain equal to the oracle's
+	{
+		++current_case;
+		const Case bc[] = { { { 512, 512, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA8 }, { { 300, 200, 0, 0 }, IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA16F },
+							{ { 64, 32, 32, 0 }, IMAGE_TYPE::IMAGE_3D | IMAGE_TYPE::R32F } };
+		std::vector<std::shared_ptr<device_image>> imgs;
+		std::vector<std::vector<uint8_t>> wants;
+		std::vector<device_image*> raw;
+		for (const auto& c : bc) {
+			const IMAGE_TYPE type = c.type | IMAGE_TYPE::FLAG_MIPMAPPED | IMAGE_TYPE::READ_WRITE;
+			const uint32_t dim[4] = { c.dim.x, c.dim.y, c.dim.z, c.dim.w };
+			const size_t l0_size = image_data_size_from_types(c.dim, type, true), all_size = image_data_size_from_types(c.dim, type);
+			std::vector<uint8_t> want(all_size), l0(l0_size);
+			flo_fill(l0.data(), dim, image_type_bits(type), 11, 0, image_layer_count(c.dim, type));
+			std::memcpy(want.data(), l0.data(), l0_size);
+			CHECK(flo_generate(want.data(), dim, image_type_bits(type), 0, 0, 8) == 0);
+			auto img = ctx.create_image(*queue, c.dim, type, MEMORY_FLAG::READ_WRITE | MEMORY_FLAG::HOST_READ_WRITE);
+			CHECK(img != nullptr);
+			if (!img) continue;
+			const uint3 extent { c.dim.x, c.dim.y, image_dim_count(type) >= 3 ? c.dim.z : 1u };
+			CHECK(img->write(*queue, l0.data(), l0.size(), { 0, 0, 0 }, extent, { 0, 0 }, { 0, 0 }));
+			imgs.push_back(img);
+			raw.push_back(img.get());
+			wants.push_back(std::move(want));
+		}
+		mip_chain_batch batch { std::span<device_image* const> { raw.data(), raw.size() } };
+		CHECK(batch.is_valid() && batch.generate(*queue));
+		for (size_t i = 0; i < imgs.size(); ++i) {
+			std::vector<uint8_t> got(wants[i].size());
+			CHECK(imgs[i]->read_levels(*queue, got.data(), got.size(), 0, imgs[i]->get_mip_level_count() - 1));
+			CHECK(got == wants[i]);
+		}
+	}
 	// constructor invariants throw (device_image.hpp:502-539); unsupported formats return nullptr (cuda_image.cpp:173-180)
 	bool threw = false;
 	try {
