@@ -466,7 +466,11 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 
 	// counters: one per tile group and one per layer, zeroed once; the kernel resets what it uses
 	const uint64_t n_groups = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2];
+#ifdef FLMIP_TIMELINE
+	const uint64_t n_counters = n_groups + im.layers + 2u + 4u + 2u * 4u * 1024u; // + 4 x u64 per CTA behind the scheduler words (tuning builds)
+#else
 	const uint64_t n_counters = n_groups + im.layers + 2u /* scheduler */;
+#endif
 	CU_TRY(cu.p_cuMemAlloc(&im.counters, n_counters * sizeof(uint32_t)), "cuMemAlloc(counters)");
 	CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, nullptr), "cuMemsetD32Async(counters)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
@@ -1154,6 +1158,19 @@ int flmip_batch_destroy(flmip_batch batch) {
 	delete batch;
 	return FLMIP_OK;
 }
+
+#ifdef FLMIP_TIMELINE
+// tuning builds only: the 4 time stamps (ns, %globaltimer) each CTA of the last single-pass launch left behind the scheduler words
+extern "C" int flmip_debug_timeline(flmip_image img, uint64_t* out, uint32_t ctas) {
+	if (check_image(img) || !out || !img->fast) return FLMIP_ERR_INVALID;
+	WITH_DEVICE(img->device)
+	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((img->fast_params.sched + 15ull) & ~7ull), (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
+	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
+	CU_TRY(cu.p_cuMemsetD8Async(((img->fast_params.sched + 15ull) & ~7ull), 0, (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
+	return FLMIP_OK;
+}
+#endif
 
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {
 	if (check_image(img)) return FLMIP_ERR_INVALID;

@@ -478,6 +478,20 @@ __device__ __forceinline__ void pdl_wait_then_release() {
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+#ifdef FLMIP_TIMELINE
+// tuning builds only (make DEFS=-DFLMIP_TIMELINE): per-CTA time stamps behind the scheduler words, read back by flmip_debug_timeline
+__device__ __forceinline__ uint64_t gtime() {
+	uint64_t t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define FLMIP_STAMP(P, slot) (reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 4u + (slot)] = gtime())
+#define FLMIP_STAMP_MAX(P, slot) atomicMax(&reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 4u + (slot)], (unsigned long long)gtime())
+#else
+#define FLMIP_STAMP(P, slot) ((void)0)
+#define FLMIP_STAMP_MAX(P, slot) ((void)0)
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -732,6 +746,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 	}
 	__syncthreads();
 	pdl_wait_then_release();
+	if (tid == 0) FLMIP_STAMP(P, 0); // CTA may touch global memory from here
 
 	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
 	// the finisher pool is idle when the consumers' in-register levels end the chain
@@ -796,6 +811,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			const GroupOf<BPP, DIMS> grp(P, tc);
 			if (arrive_last(grp.counter(P, tc.layer), grp.units(), lane)) finish_group<EK, CH, DIMS>(patch_a, patch_b, &patch_lock, P, tc, R, lane);
 		}
+		if (lane == 0) FLMIP_STAMP_MAX(P, 3); // last finisher warp of the CTA done
 		return;
 	}
 	if (warp == FLMIP_PRODUCER_WARP) {
@@ -838,6 +854,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			__syncwarp();
 		}
 		if (lane == 0) {
+			FLMIP_STAMP(P, 1); // the scheduler ran dry for this CTA: all of its loads are issued
 			// end of work: a sentinel instead of a tile
 			if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
 			stage_tile[s] = FLMIP_NO_TILE;
@@ -860,7 +877,10 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 	for (uint32_t it = 0;; ++it) {
 		mbar_wait(&full_bar[s], use & 1u);
 		const uint32_t t = stage_tile[s];
-		if (t == FLMIP_NO_TILE) break;
+		if (t == FLMIP_NO_TILE) {
+			if (tid == 0) FLMIP_STAMP(P, 2); // consumers saw the sentinel: every tile of the CTA is in registers / written
+			break;
+		}
 		const TileCoord tc = tile_coord<DIMS>(P, t);
 		const uint32_t tile_x = tc.x, tile_y = tc.y, tile_z = tc.z, layer = tc.layer;
 		const uint8_t* const tile = smem_raw + (size_t)s * TL::TILE_BYTES;
