@@ -7,7 +7,9 @@
 #define FLMIP_MAX_STAGES 8u  // upper bound of the TMA tile ring of the single-pass kernel
 // persistent single-pass CTA = 8 consumer warps + 1 TMA producer warp + FLMIP_FINISHER_WARPS finisher warps
 #define FLMIP_FINISHER_WARPS 4
+#ifndef FLMIP_SCHED_PREFETCH
 #define FLMIP_SCHED_PREFETCH 4u   // tile-index fetches the producer keeps in flight
+#endif
 #define FLMIP_UNIT_PATCH_BYTES 512u    // remainders of the tiles of one unit: at most 8 x (1 x 2 x 2 texels of 16 bytes)
 #define FLMIP_NO_TILE 0xFFFFFFFFu // end-of-work sentinel in the tile ring / cascade slots
 #define FLMIP_BLOCK_THREADS ((8 + 1 + FLMIP_FINISHER_WARPS) * 32)
