@@ -819,7 +819,10 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		// Units are handed out by a global atomic counter, so an SM that gets less memory bandwidth simply takes
 		// fewer of them.  An atomic round trip costs microseconds under load: lanes 0..PF-1 each keep one fetch in
 		// flight, lane (it % PF) holds the tile of iteration `it`.
-		constexpr uint32_t PF = FLMIP_SCHED_PREFETCH;
+		// Depth: a fetched unit is committed to this CTA, so every fetch in flight is work the last wave cannot rebalance.  A unit
+		// of 2 x 2 (x 2) tiles lasts longer than a round trip: 2 in flight (C2 +1.3 %, C5 +2.7 % over 4; 8 and 16 are slower
+		// still, profiles/r1/10_timeline.txt); single tiles need FLMIP_SCHED_PREFETCH.
+		const uint32_t PF = P.unit_shift ? 2u : FLMIP_SCHED_PREFETCH;
 		uint32_t* const sched = reinterpret_cast<uint32_t*>(P.sched);
 		// The first unit of a CTA is its own index (no round trip before the first load); the counter hands out the rest.
 		uint32_t pf = FLMIP_NO_TILE;
