@@ -415,13 +415,17 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	const uint64_t all_tiles = (uint64_t)P.tiles[0] * P.tiles[1] * P.tiles[2] * im.layers;
 	const bool units_possible = P.tiles[0] >= 2 && P.tiles[1] >= 2 && (!is3d || P.tiles[2] >= 2);
 	// Units cut the publishes (one acq_rel atomic round trip each) by 4 - 8x, but they also coarsen the work the persistent CTAs
-	// draw from the scheduler: with U units for R resident CTAs the last wave is ceil(U / R) - U / R of a unit long per CTA.
-	// Measured over image sizes (scripts/units_ab.py, profiles/r1/07_units_sweep.txt): units win when every CTA gets at most
-	// one (R / 3 <= U <= R) and when there are many (U >= 3 R; RGBA8-like formats, which are bound by the consumer warps and
-	// not by the publishes, only from 8 R on); in between (e.g. U = 512, 1.7 waves) single tiles are up to 1.8x faster.
+	// draw from the scheduler.  Measured over image sizes (scripts/units_ab.py, profiles/r1/07_units_sweep*.txt): with the
+	// scheduler prefetching only 2 units they are as good as or better than single tiles from about one unit per three CTAs on
+	// (below that single tiles use more SMs), except where there is more than one wave and the last one is mostly empty: with
+	// U work items for R resident CTAs the wave efficiency is (U / R) / ceil(U / R); single tiles are taken when theirs is
+	// more than 15 % better.
 	const uint64_t n_units = all_tiles >> im.dc, resident_ctas = 2ull * ds->info.units;
-	const bool consumer_bound = im.bpc == 8 && im.channels == 4;
-	const bool units_pay = (n_units * 3ull >= resident_ctas && n_units <= resident_ctas) || n_units >= (consumer_bound ? 8ull : 3ull) * resident_ctas;
+	auto wave_efficiency = [&](uint64_t items) {
+		const uint64_t waves = (items + resident_ctas - 1u) / resident_ctas;
+		return waves ? (double)items / (double)(waves * resident_ctas) : 0.0;
+	};
+	const bool units_pay = n_units * 3ull >= resident_ctas && (n_units <= resident_ctas || wave_efficiency(n_units) * 1.15 >= wave_efficiency(all_tiles));
 	const bool units_wanted = (flags & FLMIP_IMAGE_UNITS_ALWAYS) || (!(flags & FLMIP_IMAGE_UNITS_NEVER) && units_pay);
 	P.unit_shift = (units_possible && units_wanted) ? 1u : 0u;
 	for (int i = 0; i < 3; ++i) {
