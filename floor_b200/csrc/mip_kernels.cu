@@ -229,13 +229,28 @@ template <uint32_t EK> struct Codec {
 		if constexpr (EK == FLMIP_EK_F32) return add2_rn(mul2_sep(sub2_rn(b, a), splat2(0.5f)), a);
 		else return fma2_rn(sub2_rn(b, a), splat2(0.5f), a);
 	}
+	// unorm8 / unorm16: the encoder leaves the stored value q in the mantissa of the float 2^23 + q (bits 0x4B000000 | q) --
+	// exactly what the decoder builds with a PRMT before its FMA.  A level computed from a level this thread has just encoded
+	// can therefore decode these "magic" pairs directly and skip the byte extraction (dec2_magic(enc2_magic(v)) ==
+	// dec2_at(packed enc(v))).
+	static constexpr bool HAS_MAGIC = (EK == FLMIP_EK_UNORM8 || EK == FLMIP_EK_UNORM16);
+	static __device__ __forceinline__ f32x2_t enc2_magic(f32x2_t v, uint32_t no_double) {
+		static_assert(HAS_MAGIC, "unorm8 / unorm16 only");
+		if constexpr (EK == FLMIP_EK_UNORM8) {
+			return add2_rz(mul2_rn(v, splat2(255.0f)), splat2(MAGIC));
+		} else {
+			const f32x2_t t = no_double ? mul2_rn(v, splat2(65535.0f)) : mul2_rz(v, splat2(65535.0f));
+			return add2_rz(t, splat2(MAGIC));
+		}
+	}
+	static __device__ __forceinline__ f32x2_t dec2_magic(f32x2_t m) {
+		static_assert(HAS_MAGIC, "unorm8 / unorm16 only");
+		return fma2_rn(m, splat2(UNORM_C), splat2(-(MAGIC * UNORM_C)));
+	}
 	// storage bits of two elements; bits above the storage width are unspecified
 	static __device__ __forceinline__ void enc2_dirty(f32x2_t v, uint32_t& lo, uint32_t& hi, uint32_t no_double) {
-		if constexpr (EK == FLMIP_EK_UNORM8) {
-			unpk2(add2_rz(mul2_rn(v, splat2(255.0f)), splat2(MAGIC)), lo, hi);
-		} else if constexpr (EK == FLMIP_EK_UNORM16) {
-			const f32x2_t t = no_double ? mul2_rn(v, splat2(65535.0f)) : mul2_rz(v, splat2(65535.0f));
-			unpk2(add2_rz(t, splat2(MAGIC)), lo, hi);
+		if constexpr (HAS_MAGIC) {
+			unpk2(enc2_magic(v, no_double), lo, hi);
 		} else {
 			uint32_t a, b;
 			unpk2(v, a, b);
@@ -267,6 +282,27 @@ template <uint32_t EK> struct Codec {
 				uint32_t a, b, c, d;
 				enc2_dirty(v[p], a, b, no_double);
 				enc2_dirty(v[p + 1], c, d, no_double);
+				out[p >> 1] = __byte_perm(__byte_perm(a, b, 0x0040u), __byte_perm(c, d, 0x0040u), 0x5410u);
+			}
+		}
+	}
+
+	// pack NP already encoded "magic" pairs (unorm8 / unorm16) into words
+	template <int NP> static __device__ __forceinline__ void pack2_magic(const f32x2_t (&m)[NP], uint32_t* out) {
+		static_assert(HAS_MAGIC && BYTES <= 2, "unorm8 / unorm16 only");
+		if constexpr (BYTES == 2) {
+#pragma unroll
+			for (int p = 0; p < NP; ++p) {
+				uint32_t a, b;
+				unpk2(m[p], a, b);
+				out[p] = __byte_perm(a, b, 0x5410u);
+			}
+		} else {
+#pragma unroll
+			for (int p = 0; p < NP; p += 2) {
+				uint32_t a, b, c, d;
+				unpk2(m[p], a, b);
+				unpk2(m[p + 1], c, d);
 				out[p >> 1] = __byte_perm(__byte_perm(a, b, 0x0040u), __byte_perm(c, d, 0x0040u), 0x5410u);
 			}
 		}
@@ -364,6 +400,41 @@ __device__ __forceinline__ void reduce_rows_2d(const uint32_t (&r0)[NW], const u
 		}
 		C::template enc_pack<NO>(v, out, no_double);
 	}
+}
+
+// unorm8 / unorm16: the same, also handing out the encoded result as "magic" pairs (see Codec::enc2_magic) ...
+template <uint32_t EK, int CH, int NW>
+__device__ __forceinline__ void reduce_rows_2d_keep(const uint32_t (&r0)[NW], const uint32_t (&r1)[NW], uint32_t (&out)[NW / 2],
+													f32x2_t (&kept)[NW / Codec<EK>::BYTES], uint32_t no_double) {
+	using C = Codec<EK>;
+	constexpr int NO = NW * 2 / C::BYTES;
+	static_assert(NO >= CH && (NO % CH) == 0 && (NO % 2) == 0, "row must hold at least one x pair");
+#pragma unroll
+	for (int p = 0; p < NO / 2; ++p) {
+		const int e0 = 2 * p, e1 = 2 * p + 1;
+		const int ea0 = (2 * (e0 / CH)) * CH + (e0 % CH), eb0 = ea0 + CH, ea1 = (2 * (e1 / CH)) * CH + (e1 % CH), eb1 = ea1 + CH;
+		const f32x2_t x0 = C::lerp_half2(C::dec2_at(r0, ea0, ea1), C::dec2_at(r0, eb0, eb1));
+		const f32x2_t x1 = C::lerp_half2(C::dec2_at(r1, ea0, ea1), C::dec2_at(r1, eb0, eb1));
+		kept[p] = C::enc2_magic(C::lerp_half2(x0, x1), no_double);
+	}
+	C::template pack2_magic<NO / 2>(kept, out);
+}
+// ... and the next level from two rows of such pairs (NP pairs = NP * 2 / CH texels per row, CH >= 2: a pair never spans texels)
+template <uint32_t EK, int CH, int NP>
+__device__ __forceinline__ void reduce_magic_2d(const f32x2_t (&m0)[NP], const f32x2_t (&m1)[NP], uint32_t (&out)[NP * Codec<EK>::BYTES / 4],
+												uint32_t no_double) {
+	using C = Codec<EK>;
+	constexpr int PPT = CH / 2; // pairs per texel
+	static_assert(CH >= 2 && (NP % (2 * PPT)) == 0, "whole x pairs of texels");
+	f32x2_t v[NP / 2];
+#pragma unroll
+	for (int p = 0; p < NP / 2; ++p) {
+		const int a = (2 * (p / PPT)) * PPT + (p % PPT), b = a + PPT;
+		const f32x2_t x0 = C::lerp_half2(C::dec2_magic(m0[a]), C::dec2_magic(m0[b]));
+		const f32x2_t x1 = C::lerp_half2(C::dec2_magic(m1[a]), C::dec2_magic(m1[b]));
+		v[p] = C::enc2_magic(C::lerp_half2(x0, x1), no_double);
+	}
+	C::template pack2_magic<NP / 2>(v, out);
 }
 
 // r[z][y]: rows (y, y+1) of slices (z, z+1)
@@ -908,12 +979,22 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			if (lane == 0) mbar_arrive(&empty_bar[s]);
 
 			uint32_t l1[2][4]; // two level-1 rows of 16 bytes, logical (left, right) order
+			// unorm8 / unorm16 texels of 2 .. 4 bytes with >= 2 channels (RGBA8, RG8, RG16): level 2 of a 16-byte chunk depends on
+			// that chunk alone and is computed from the encoder's own "magic" pairs of level 1 (no byte extraction)
+			constexpr bool MAGIC_L2 = C::HAS_MAGIC && CH >= 2 && BPP <= 4;
+			constexpr int MNP = MAGIC_L2 ? 4 / C::BYTES : 1;
+			f32x2_t mg[2][2][MNP]; // [level-1 row][chunk][pair]
 			if constexpr (!WIDE) {
 #pragma unroll
 				for (int j = 0; j < 2; ++j) {
 					uint32_t o0[2], o1[2];
-					reduce_rows_2d<EK, CH, 4>(raw[2 * j][0], raw[2 * j + 1][0], o0, P.no_double);
-					reduce_rows_2d<EK, CH, 4>(raw[2 * j][1], raw[2 * j + 1][1], o1, P.no_double);
+					if constexpr (MAGIC_L2) {
+						reduce_rows_2d_keep<EK, CH, 4>(raw[2 * j][0], raw[2 * j + 1][0], o0, mg[j][0], P.no_double);
+						reduce_rows_2d_keep<EK, CH, 4>(raw[2 * j][1], raw[2 * j + 1][1], o1, mg[j][1], P.no_double);
+					} else {
+						reduce_rows_2d<EK, CH, 4>(raw[2 * j][0], raw[2 * j + 1][0], o0, P.no_double);
+						reduce_rows_2d<EK, CH, 4>(raw[2 * j][1], raw[2 * j + 1][1], o1, P.no_double);
+					}
 					l1[j][0] = sel ? o1[0] : o0[0]; l1[j][1] = sel ? o1[1] : o0[1];
 					l1[j][2] = sel ? o0[0] : o1[0]; l1[j][3] = sel ? o0[1] : o1[1];
 				}
@@ -942,7 +1023,15 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 				// level 2 in registers: 8 bytes per thread
 				if (P.level_count > 2) {
 					uint32_t l2[2];
-					reduce_rows_2d<EK, CH, 4>(l1[0], l1[1], l2, P.no_double);
+					if constexpr (MAGIC_L2) {
+						uint32_t w0[1], w1[1];
+						reduce_magic_2d<EK, CH, MNP>(mg[0][0], mg[1][0], w0, P.no_double);
+						reduce_magic_2d<EK, CH, MNP>(mg[0][1], mg[1][1], w1, P.no_double);
+						l2[0] = sel ? w1[0] : w0[0];
+						l2[1] = sel ? w0[0] : w1[0];
+					} else {
+						reduce_rows_2d<EK, CH, 4>(l1[0], l1[1], l2, P.no_double);
+					}
 					uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
 					const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
 					const uint32_t row = tile_y * (TL::TY / 4) + ty;
