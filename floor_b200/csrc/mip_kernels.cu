@@ -512,6 +512,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { // raises the transaction count only; the arrival follows
+	asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 	// try_wait suspends the thread in hardware until the phase completes or a time limit expires.  Without a hint that limit
 	// is short and the waiting warps (the producer, four mostly idle finisher warps per CTA) re-issue try_wait + branch all
@@ -796,6 +799,9 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 	__shared__ uint32_t finisher_ticket, patch_lock, unit_count[2];
 	__shared__ __align__(16) uint8_t unit_patch[2][FLMIP_UNIT_PATCH_BYTES + FLMIP_UNIT_PATCH_BYTES / 4u];
 	__shared__ uint32_t stage_tile[FLMIP_MAX_STAGES], slot_tile[FLMIP_FINISHER_WARPS]; // tile index riding along with the data
+	// ... and where the tile's part of level 1 ([0]) and level 2 ([1], 2D) starts in global memory: computed once per tile by the
+	// producer instead of by every consumer thread (tile index -> coordinates -> 64-bit level / layer / row offsets)
+	__shared__ __align__(16) uint64_t stage_org[FLMIP_MAX_STAGES][2];
 	const uint32_t stages = P.stages;
 	uint8_t* const cascade_base = smem_raw + (size_t)stages * TL::TILE_BYTES;
 
@@ -911,11 +917,23 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 					const uint32_t t = (u << kbits) | k;
 					if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
 					const TileCoord tc = tile_coord<DIMS>(P, t);
-					stage_tile[s] = t;
-					mbar_arrive_expect_tx(&full_bar[s], TL::TILE_BYTES);
+					// the load first, then (behind its latency) what rides along with it; the arrival releases both to the consumers
+					mbar_expect_tx(&full_bar[s], TL::TILE_BYTES);
 					// innermost coordinate in uint32 units; 2D images use the third tensor dim for the layer
 					tma_load_3d(smem_raw + (size_t)s * TL::TILE_BYTES, &tmap, &full_bar[s], (int)(tc.x * (ROW_BYTES / 4)), (int)(tc.y * TL::TY),
 								(int)(DIMS == 3 ? tc.z * TL::TZ : tc.layer));
+					stage_tile[s] = t;
+					{
+						const uint64_t l1_pitch = (uint64_t)(P.dim[0] >> 1) * BPP;
+						const uint64_t row1 = (DIMS == 3 ? (uint64_t)tc.z * (TL::TZ / 2) * (P.dim[1] >> 1) : 0ull) + (uint64_t)tc.y * (TL::TY / 2);
+						stage_org[s][0] = reinterpret_cast<uint64_t>(level_layer_ptr<BPP, DIMS>(P, 1, tc.layer)) + row1 * l1_pitch + (uint64_t)tc.x * (ROW_BYTES / 2);
+						if constexpr (DIMS == 2) {
+							const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
+							stage_org[s][1] = reinterpret_cast<uint64_t>(level_layer_ptr<BPP, DIMS>(P, 2, tc.layer)) + (uint64_t)tc.y * (TL::TY / 4) * l2_pitch +
+											  (uint64_t)tc.x * (ROW_BYTES / 4);
+						}
+					}
+					mbar_arrive(&full_bar[s]);
 					if (++s == stages) { s = 0; ++use; }
 				}
 			}
@@ -955,11 +973,10 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			if (tid == 0) FLMIP_STAMP(P, 2); // consumers saw the sentinel: every tile of the CTA is in registers / written
 			break;
 		}
-		const TileCoord tc = tile_coord<DIMS>(P, t);
-		const uint32_t tile_x = tc.x, tile_y = tc.y, tile_z = tc.z, layer = tc.layer;
 		const uint8_t* const tile = smem_raw + (size_t)s * TL::TILE_BYTES;
 		uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
-		uint8_t* const g1 = level_layer_ptr<BPP, DIMS>(P, 1, layer);
+		const ulonglong2 org = *reinterpret_cast<const ulonglong2*>(stage_org[s]); // read before the stage is handed back
+		uint8_t* const g1 = reinterpret_cast<uint8_t*>(org.x);     // the tile's part of level 1
 		const uint64_t l1_pitch = (uint64_t)(P.dim[0] >> 1) * BPP; // bytes per level-1 row
 
 		if constexpr (DIMS == 2) {
@@ -1015,8 +1032,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			// level 1: one 16-byte store per row
 #pragma unroll
 			for (int j = 0; j < 2; ++j) {
-				const uint32_t row = tile_y * (TL::TY / 2) + 2 * ty + j;
-				*reinterpret_cast<uint4*>(g1 + (uint64_t)row * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
+				*reinterpret_cast<uint4*>(g1 + (uint64_t)(2 * ty + j) * l1_pitch + tx * 16) =
 					make_uint4(l1[j][0], l1[j][1], l1[j][2], l1[j][3]);
 			}
 			if constexpr (!WIDE) {
@@ -1032,10 +1048,9 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 					} else {
 						reduce_rows_2d<EK, CH, 4>(l1[0], l1[1], l2, P.no_double);
 					}
-					uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
+					uint8_t* const g2 = reinterpret_cast<uint8_t*>(org.y);
 					const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
-					const uint32_t row = tile_y * (TL::TY / 4) + ty;
-					*reinterpret_cast<uint2*>(g2 + (uint64_t)row * l2_pitch + (uint64_t)tile_x * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
+					*reinterpret_cast<uint2*>(g2 + (uint64_t)ty * l2_pitch + tx * 8) = make_uint2(l2[0], l2[1]);
 					if (need_finish) {
 						if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
 						*reinterpret_cast<uint2*>(buf_a + ty * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
@@ -1055,10 +1070,9 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 					if (!(lane & 1u)) {
 						uint32_t l2[4];
 						reduce_rows_2d<EK, CH, 8>(ra, rb, l2, P.no_double);
-						uint8_t* const g2 = level_layer_ptr<BPP, DIMS>(P, 2, layer);
+						uint8_t* const g2 = reinterpret_cast<uint8_t*>(org.y);
 						const uint64_t l2_pitch = (uint64_t)(P.dim[0] >> 2) * BPP;
-						const uint32_t row = tile_y * (TL::TY / 4) + ty;
-						*reinterpret_cast<uint4*>(g2 + (uint64_t)row * l2_pitch + (uint64_t)tile_x * (ROW_BYTES / 4) + (tx >> 1) * 16) =
+						*reinterpret_cast<uint4*>(g2 + (uint64_t)ty * l2_pitch + (tx >> 1) * 16) =
 							make_uint4(l2[0], l2[1], l2[2], l2[3]);
 						if (need_finish) {
 							if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
@@ -1106,9 +1120,8 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 						}
 				reduce_rows_3d<EK, CH, 8>(rr[0][0], rr[0][1], rr[1][0], rr[1][1], l1, P.no_double);
 			}
-			const uint32_t row = tile_y * (TL::TY / 2) + ty, slice = tile_z * (TL::TZ / 2) + tz;
 			const uint64_t l1_rows = P.dim[1] >> 1;
-			*reinterpret_cast<uint4*>(g1 + ((uint64_t)slice * l1_rows + row) * l1_pitch + (uint64_t)tile_x * (ROW_BYTES / 2) + tx * 16) =
+			*reinterpret_cast<uint4*>(g1 + ((uint64_t)tz * l1_rows + ty) * l1_pitch + tx * 16) =
 				make_uint4(l1[0], l1[1], l1[2], l1[3]);
 			if (need_finish) {
 				if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
