@@ -1238,9 +1238,10 @@ __device__ __forceinline__ void generic_texel(const flmip_generic_params& P, uin
 // memory; the host cuts a launch short where texel 2 would lie outside a 2-texel-wide remainder.  Partial tiles at
 // the image border are masked.  Every level is re-decoded from its stored (quantised) bits.
 // ------------------------------------------------------------------------------------------------------
-struct axis_f {
+struct __align__(16) axis_f {
 	float t;       // weight of B
 	uint32_t a, b; // texel indices of A (outside) and B (active) in the source level
+	uint32_t pad;  // 16 bytes: one LDS.128 per table entry
 };
 // Same values as the literal replay in generic_texel(), computed without the quarter-rate XU pipe and without fmodf:
 // for 0 <= x < 2^23, x + 2^23 rounded toward zero holds floor(x) in its mantissa (the codecs use the same identity),
@@ -1348,6 +1349,36 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 	if constexpr (D == 3) { ti[2] = tile % P.tiles[2]; tile /= P.tiles[2]; }
 	const uint32_t layer = tile;
 	uint8_t* const base = reinterpret_cast<uint8_t*>(P.base);
+
+	// ---- sampler table of the tile: (A, B, t) of every destination row / column / slice of every level this launch produces,
+	//      computed once per CTA (126 entries in 2D) instead of by every thread for its own texels.  Heap layout per axis: level k
+	//      holds its T >> k entries at [T >> k, 2 * (T >> k)).  Level 1 keeps A and B as texel indices of the source level (they
+	//      address global memory), levels >= 2 as indices into the tile's part of level k - 1 in shared memory (the host guarantees
+	//      they lie inside the tile's remainder).  Touches only kernel parameters and shared memory: runs before the PDL wait.
+	__shared__ axis_f axtab[D][64];
+	{
+		constexpr uint32_t TD[3] = { (uint32_t)G::TX, (uint32_t)G::TY, (uint32_t)G::TZ };
+		constexpr uint32_t TOTAL = G::TX + G::TY + (D == 3 ? G::TZ : 0);
+		for (uint32_t idx = t; idx < TOTAL; idx += THREADS) {
+			uint32_t d = 0, j = idx;
+			if (j >= TD[0]) { j -= TD[0]; d = 1; }
+			if (D == 3 && d == 1 && j >= TD[1]) { j -= TD[1]; d = 2; }
+			if (j == 0) continue; // heap slot 0 is unused
+			const uint32_t td = (d == 0 ? TD[0] : (d == 1 ? TD[1] : TD[2]));
+			const uint32_t k = (uint32_t)__clz(j) - (uint32_t)__clz(td); // level: T >> k <= j < 2 * (T >> k)
+			if (k > P.nlev || P.dim[k][d] == 0u) continue;
+			const uint32_t e = td >> k, pe = 2u * e;                    // extents of levels k and k - 1 of the tile
+			const uint32_t g = min(ti[d] * e + (j - e), P.dim[k][d] - 1u); // destination index (clamped: partial tiles are masked later)
+			axis_f f = axis_fetch(g, P.inv_prev[k - 1][d], P.fdim[k - 1][d], P.fdim_excl[k - 1][d]);
+			if (k >= 2u) {
+				f.a = min(f.a - ti[d] * pe, pe - 1u);
+				f.b = min(f.b - ti[d] * pe, pe - 1u);
+			}
+			f.pad = 0u;
+			axtab[d][j] = f;
+		}
+	}
+	__syncthreads();
 	pdl_wait_then_release();
 
 	// ---- level 1: straight from global memory (each warp reads whole 2 * BPP * 32 byte row segments) -------------
@@ -1366,11 +1397,8 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 		static_assert(THREADS % EX == 0 && (D < 3 || THREADS % (EX * EY) == 0), "loop-invariant axes");
 		constexpr int INV = (D == 3 ? 2 : 1); // number of loop-invariant axes
 		axis_f fix[INV];
-		fix[0] = axis_fetch(min(ti[0] * EX + t % EX, W1 - 1u), P.inv_prev[0][0], P.fdim[0][0], P.fdim_excl[0][0]);
-		if constexpr (D == 3) fix[1] = axis_fetch(min(ti[1] * EY + (t / EX) % EY, H1 - 1u), P.inv_prev[0][1], P.fdim[0][1], P.fdim_excl[0][1]);
-		// 2D: the warp's four rows are fetched once by lanes 0..3 and handed round with shuffles
-		axis_f rowf = { 0.0f, 0u, 0u };
-		if constexpr (D == 2) rowf = axis_fetch(min(ti[1] * EY + warp * PER_THREAD + (lane & 3u), H1 - 1u), P.inv_prev[0][1], P.fdim[0][1], P.fdim_excl[0][1]);
+		fix[0] = axtab[0][EX + t % EX];
+		if constexpr (D == 3) fix[1] = axtab[1][EY + (t / EX) % EY];
 		const uint64_t pitch = (uint64_t)W0 * BPP;
 		const uint32_t xoff[2] = { fix[0].a * BPP, fix[0].b * BPP };
 #pragma unroll 1
@@ -1388,17 +1416,14 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 				uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
 				wt[u][0] = fix[0].t;
 				if constexpr (D == 2) {
-					wt[u][1] = __shfl_sync(0xFFFFFFFFu, rowf.t, c + u);
-					s[1][0] = __shfl_sync(0xFFFFFFFFu, rowf.a, c + u);
-					s[1][1] = __shfl_sync(0xFFFFFFFFu, rowf.b, c + u);
+					const axis_f f = axtab[1][EY + oy]; // the same row for the whole warp: a broadcast read
+					wt[u][1] = f.t; s[1][0] = f.a; s[1][1] = f.b;
 				} else {
 					wt[u][1] = fix[1].t; s[1][0] = fix[1].a; s[1][1] = fix[1].b;
+					const axis_f f = axtab[2][G::TZ / 2 + oz];
+					wt[u][D - 1] = f.t; s[2][0] = f.a; s[2][1] = f.b;
 				}
 				if (ok[u]) {
-					if constexpr (D == 3) {
-						const axis_f f = axis_fetch(g[u][2], P.inv_prev[0][2], P.fdim[0][2], P.fdim_excl[0][2]);
-						wt[u][D - 1] = f.t; s[2][0] = f.a; s[2][1] = f.b;
-					}
 #pragma unroll
 					for (int r = 0; r < (1 << (D - 1)); ++r) {
 						// one row pointer per (y, z) choice, two texels (A, B along x) from it
@@ -1432,14 +1457,14 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 		const uint32_t g[3] = { ti[0] * ex + ox, ti[1] * ey + oy, (D == 3 ? ti[2] * ez + oz : 0u) };
 		if (g[0] < P.dim[k][0] && g[1] < P.dim[k][1] && (D < 3 || g[2] < P.dim[k][2])) {
 			const uint32_t pe[3] = { 2u * ex, 2u * ey, 2u * ez }; // extents of level k - 1 of the tile
+			const uint32_t ext[3] = { ex, ey, ez }, oo[3] = { ox, oy, oz };
 			axis_f af[D];
 			uint32_t s[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
 #pragma unroll
 			for (int d = 0; d < D; ++d) {
-				af[d] = axis_fetch(g[d], P.inv_prev[k - 1][d], P.fdim[k - 1][d], P.fdim_excl[k - 1][d]);
-				// tile-local indices in level k - 1 (the host guarantees they lie inside the tile's remainder)
-				s[d][0] = min(af[d].a - ti[d] * pe[d], pe[d] - 1u);
-				s[d][1] = min(af[d].b - ti[d] * pe[d], pe[d] - 1u);
+				af[d] = axtab[d][ext[d] + oo[d]]; // A, B: tile-local indices in level k - 1
+				s[d][0] = af[d].a;
+				s[d][1] = af[d].b;
 			}
 			uint32_t raw[1 << D][NW];
 #pragma unroll
