@@ -1597,10 +1597,13 @@ FLMIP_FAST_KERNELS_FOR_KIND(10)
 FLMIP_FAST_KERNELS_FOR_KIND(11)
 #endif
 
-// 2D, texels below 16 bytes: 5 CTAs per SM (48 registers, at most 8 bytes of spills) -- the tile kernel is latency-bound there;
-// measured on N2 (RGBA16F): 4 CTAs 4 818 GB/s, 5 CTAs 5 018 GB/s, 6 CTAs 4 696 GB/s.  3D and 16-byte texels keep ptxas' choice
-// (they would spill 16 .. 200 bytes).
-#define FLMIP_TILE_MIN_BLOCKS(D, K, CHN) (((D) == 2 && flmip_elem_bytes(K) * (CHN) < 16) ? 5 : 1)
+// 2D, texels below 16 bytes: 4 CTAs per SM (64 registers, no spills).  Measured on N2 (RGBA16F) with the per-CTA sampler table:
+// 3 CTAs 5 175 GB/s, 4 CTAs 5 645, 5 CTAs (48 registers, 16 bytes of spills) 5 315, 6 CTAs 5 354 (profiles/r1/15_tile_sampler_table_ab.txt;
+// before the table the kernel executed twice the instructions and 5 CTAs were best).  3D and 16-byte texels keep ptxas' choice.
+#ifndef FLMIP_TILE2D_MIN_BLOCKS
+#define FLMIP_TILE2D_MIN_BLOCKS 4
+#endif
+#define FLMIP_TILE_MIN_BLOCKS(D, K, CHN) (((D) == 2 && flmip_elem_bytes(K) * (CHN) < 16) ? FLMIP_TILE2D_MIN_BLOCKS : 1)
 #define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
 	extern "C" __global__ void __launch_bounds__(256, FLMIP_TILE_MIN_BLOCKS(D, K, CHN)) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
 		tile_body<K, CHN, D>(P);                                                                                                 \
