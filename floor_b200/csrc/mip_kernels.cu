@@ -1596,11 +1596,19 @@ FLMIP_FAST_KERNELS_FOR_KIND(11)
 
 // 2D, texels below 16 bytes: 4 CTAs per SM (64 registers, no spills).  Measured on N2 (RGBA16F) with the per-CTA sampler table:
 // 3 CTAs 5 175 GB/s, 4 CTAs 5 645, 5 CTAs (48 registers, 16 bytes of spills) 5 315, 6 CTAs 5 354 (profiles/r1/15_tile_sampler_table_ab.txt;
-// before the table the kernel executed twice the instructions and 5 CTAs were best).  3D and 16-byte texels keep ptxas' choice.
+// before the table the kernel executed twice the instructions and 5 CTAs were best).  The same 4 CTAs (64 registers, no spills) for 16-byte
+// texels (ptxas' own choice: 72 registers, 3 CTAs; NPOT RGBA32F layers +2 %) and for volumes (ptxas: 74 .. 90 registers, 2 CTAs; 500 x 300 x 200:
+// R32F +10 %, RGBA8 +22 %, RGBA16F +30 %; scripts/tile_occ_ab.py, same log).
 #ifndef FLMIP_TILE2D_MIN_BLOCKS
 #define FLMIP_TILE2D_MIN_BLOCKS 4
 #endif
-#define FLMIP_TILE_MIN_BLOCKS(D, K, CHN) (((D) == 2 && flmip_elem_bytes(K) * (CHN) < 16) ? FLMIP_TILE2D_MIN_BLOCKS : 1)
+#ifndef FLMIP_TILE2D_WIDE_MIN_BLOCKS
+#define FLMIP_TILE2D_WIDE_MIN_BLOCKS 4
+#endif
+#ifndef FLMIP_TILE3D_MIN_BLOCKS
+#define FLMIP_TILE3D_MIN_BLOCKS 4
+#endif
+#define FLMIP_TILE_MIN_BLOCKS(D, K, CHN) ((D) == 3 ? FLMIP_TILE3D_MIN_BLOCKS : (flmip_elem_bytes(K) * (CHN) < 16 ? FLMIP_TILE2D_MIN_BLOCKS : FLMIP_TILE2D_WIDE_MIN_BLOCKS))
 #define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
 	extern "C" __global__ void __launch_bounds__(256, FLMIP_TILE_MIN_BLOCKS(D, K, CHN)) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
 		tile_body<K, CHN, D>(P);                                                                                                 \
