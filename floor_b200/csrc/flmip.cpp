@@ -65,7 +65,7 @@ driver_api cu;
 
 struct device_state {
 	CUdevice dev = 0;
-	CUcontext ctx = nullptr;
+	std::atomic<CUcontext> ctx { nullptr }; // retained on first use (double-checked under mtx)
 	CUmodule module = nullptr;
 	std::mutex mtx;
 	std::unordered_map<std::string, CUfunction> functions;
@@ -166,13 +166,13 @@ int get_device(int device, device_state** out) {
 	if (rc != FLMIP_OK) return rc;
 	if (device < 0 || (size_t)device >= devices.size()) return fail(FLMIP_ERR_INVALID, "invalid device index %d (have %zu)", device, devices.size());
 	device_state* ds = devices[(size_t)device];
-	if (!ds->ctx) {
+	if (!ds->ctx.load(std::memory_order_acquire)) {
 		std::lock_guard<std::mutex> lock(ds->mtx);
-		if (!ds->ctx) {
+		if (!ds->ctx.load(std::memory_order_relaxed)) {
 			// primary context: shared with any CUDA-runtime user in the process (floor creates its own: cuda_context.cpp:117-124)
 			CUcontext ctx = nullptr;
 			CU_TRY(cu.p_cuDevicePrimaryCtxRetain(&ctx, ds->dev), "cuDevicePrimaryCtxRetain");
-			ds->ctx = ctx;
+			ds->ctx.store(ctx, std::memory_order_release);
 		}
 	}
 	*out = ds;
@@ -183,7 +183,7 @@ int get_device(int device, device_state** out) {
 struct ctx_guard {
 	bool pushed = false;
 	int push(device_state* ds) {
-		CU_TRY(cu.p_cuCtxPushCurrent(ds->ctx), "cuCtxPushCurrent");
+		CU_TRY(cu.p_cuCtxPushCurrent(ds->ctx.load(std::memory_order_acquire)), "cuCtxPushCurrent");
 		pushed = true;
 		return FLMIP_OK;
 	}
@@ -964,7 +964,7 @@ int flmip_device_cu_context(int device, void** out) {
 	device_state* ds = nullptr;
 	const int rc = get_device(device, &ds);
 	if (rc != FLMIP_OK) return rc;
-	*out = ds->ctx;
+	*out = ds->ctx.load(std::memory_order_acquire);
 	return FLMIP_OK;
 }
 
