@@ -7,14 +7,18 @@
 A "step" is one full mip chain (device_image::generate_mip_map_chain) over one batch of synthetic input.
 Workload at every N: one BASELINE `configs[1]` image (8192x8192 RGBA16F 2D, 14 levels) per GPU -- the path does not
 split a single 2D image ("a single 2D image stays on one GPU"), so N GPUs run N independent textures (weak scaling,
-no collective, NCCL only carries the barrier and the max-over-ranks of the device time).  `--workload c3|c4` run the
-layered configs with layers / cubes sharded across ranks instead.
+no collective, NCCL only carries the barrier and the max-over-ranks of the device time).  The same line also carries
+`layered`: BASELINE configs 3 and 4 with their layers / cubes sharded across the N ranks (strong scaling: total work fixed),
+timed the same way, and `parity_check`: what the timed launches wrote, compared with the oracle (whole chain for the
+single images, >= 16 sampled layers / faces per GPU for the layered ones).  `--workload c3|c4|...` makes another
+workload the headline of the line instead (tuning runs).
 
 Metric = algorithmic bytes (level 0 read once + every generated level written once) per second, SURVEY.md 8(d).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -119,81 +123,146 @@ def shard_layers(total: int, world: int, rank: int, multiple: int = 1):
     return lo * multiple, (hi - lo) * multiple
 
 
-def algorithmic_bytes(oracle_free_sizes):
-    return int(sum(oracle_free_sizes))
+L2_BYTES = 126 << 20
 
 
-def run_ours(args, rank, world, local_rank):
-    import floor_b200
-    desc, dim, t, sharded, cid = WORKLOADS[args.workload]
-    ctx = floor_b200.device_context()
-    dev = ctx.get_device(local_rank)
-    q = ctx.create_queue(dev)
-    lib = floor_b200.lib()
-
-    # per-rank image: the whole workload image, or this rank's contiguous layer range of it
-    layer_id0 = 0
-    rdim = list(dim)
+def workload_geometry(workload: str, world: int = 1, rank: int = 0, layers_override: int = 0):
+    """(per-rank image dim, global id of its first layer, levels, algorithmic bytes of the per-rank image) -- host arithmetic only
+    (floor_b200.image_types mirrors image_types.hpp), so both arms print the same `config` without touching a GPU"""
+    from floor_b200 import image_types as it
+    desc, dim, t, sharded, cid = WORKLOADS[workload]
+    rdim, layer_id0 = list(dim), 0
     if sharded:
-        is_cube = bool(t & T.FLAG_CUBE)
-        total_layers = args.layers or dim[2]
-        lo, n = shard_layers(total_layers, world, rank)
+        lo, n = shard_layers(layers_override or dim[2], world, rank)
         rdim[2] = n
-        layer_id0 = lo * (6 if is_cube else 1)
-    n_images = 2 if not sharded else 1  # images of the end-to-end leg (one queue each)
-    images = [ctx.create_image(q, tuple(rdim), t) for _ in range(n_images)]
-    for i, im in enumerate(images):
-        im.fill_synthetic(q, cid, layer_id0 if sharded else rank * n_images + i)
-    q.finish()
-    img = images[0]
-    # resident leg: rotate over enough images that a step never finds its input (or a previous output) in the 126 MB L2:
-    # at least two, and at least 2 x L2 worth of them for the small workloads (C1: 46 images of 5.6 MB)
-    L2_BYTES = 126 << 20
-    n_rot = n_images if sharded else int(min(64, max(2, -(-2 * L2_BYTES // img.image_data_size_mip_maps))))
-    rot = list(images)
-    for i in range(len(rot), n_rot):
-        im = ctx.create_image(q, tuple(rdim), t)
-        im.fill_synthetic(q, cid, rank * n_rot + i)
+        layer_id0 = lo * (6 if t & T.FLAG_CUBE else 1)
+    d4 = tuple(rdim) + (0,) * (4 - len(rdim))
+    return tuple(rdim), layer_id0, it.mip_level_count(d4, t), it.image_data_size(d4, t)
+
+
+def config_for(workload: str, world: int, layers_override: int = 0):
+    """the `config` object of the JSON line: a pure function of (workload, N), identical for `--impl ours` and `--impl reference`"""
+    desc, dim, t, sharded, cid = WORKLOADS[workload]
+    _, _, levels, alg = workload_geometry(workload, world, 0, layers_override)
+    n_rot = 1 if sharded else int(min(64, max(2, -(-2 * L2_BYTES // alg))))
+    return {"workload": desc + (f"; one such image per GPU ({world} independent textures)" if not sharded and world > 1 else ""),
+            "levels": levels, "algorithmic_bytes_per_gpu_step": alg,
+            "l2": ("working set per step (%.0f MB) exceeds the 126 MB L2" % (alg / 1e6) if alg > L2_BYTES else
+                   "inputs rotate over %d images (%.0f MB in total, more than twice the 126 MB L2)" % (n_rot, n_rot * alg / 1e6))
+                  + ("; steps rotate over %d images" % n_rot if n_rot > 1 and alg > L2_BYTES else ""),
+            "parallelism": "independent images per GPU, no collective" if not sharded else "contiguous layer ranges per GPU, no collective"}
+
+
+def sampled_layers(n_layers: int, count: int = 16, seed: int = 0x5EED):
+    """first, last and seeded picks"""
+    picks = {0, n_layers - 1}
+    rng = np.random.default_rng(seed)
+    while len(picks) < min(count, n_layers):
+        picks.add(int(rng.integers(0, n_layers)))
+    return sorted(picks)
+
+
+def parity_check(img, q, workload: str, fill_id: int, layered: bool):
+    """Looks at what the timed launches wrote (the oracle is only the checker here): the whole chain of a single image, or >= 16
+    sampled layers / faces (first, last, seeded picks) of a layered one, every level, bit-exact against the oracle run per layer
+    (device_image.cpp:304-327: layers are independent chains).  `fill_id` = config id's layer id the image was filled with."""
+    import oracle
+    desc, dim, t, sharded, cid = WORKLOADS[workload]
+    threads = min(os.cpu_count() or 8, 32)
+    mismatches, checked = 0, 0
+    if not layered:
+        rdim = img.image_dim[: len(dim)]
+        got = img.download_levels(q)
+        n0 = img.levels[0]["size"]
+        l0 = oracle.fill_synthetic(rdim, t, cid, layer_id0=fill_id)
+        ok = bool(np.array_equal(got[:n0], l0))
+        if ok:
+            want = oracle.generate_mip_map_chain(l0, rdim, t, threads=threads)
+            ok = hashlib.sha256(got.tobytes()).digest() == hashlib.sha256(want.tobytes()).digest()
+        return {"layers_checked": 1, "mismatches": 0 if ok else 1, "scope": "whole image, every level, sha256 vs oracle"}
+    fmt_bits = t & ~(T.IMAGE_2D_ARRAY | T.IMAGE_CUBE_ARRAY | T.FLAG_CUBE | T.FLAG_ARRAY)
+    t1 = T.IMAGE_2D | fmt_bits
+    dim2d = dim[:2]
+    picks = sampled_layers(img.layer_count)
+    for layer in picks:
+        got = img.download_layers(q, layer, 1)
+        l0 = oracle.fill_synthetic(dim2d, t1, cid, layer_id0=fill_id + layer, layer_num=1)
+        want = oracle.generate_mip_map_chain(l0, dim2d, t1, threads=threads)
+        checked += 1
+        if not np.array_equal(got, want):
+            mismatches += 1
+    return {"layers_checked": checked, "mismatches": mismatches,
+            "scope": f"layers {picks[0]}, {picks[-1]} and seeded picks of this rank's {img.layer_count}, every level, bit-exact vs oracle"}
+
+
+class Ranks:
+    """torch.distributed (NCCL) carries the barrier and the max / sum over ranks of the timings -- nothing else"""
+
+    def __init__(self, world, local_rank):
+        self.world, self.dist, self.torch = world, None, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl")
+            self.dist, self.torch = dist, torch
+
+    def barrier(self, q=None):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+        if q is not None:
+            q.finish()
+
+    def reduce(self, values, op="max"):
+        if self.dist is None:
+            return [float(v) for v in values]
+        tt = self.torch.tensor([float(v) for v in values], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in tt]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, layers_override=0, sampler=None, keep=1):
+    """Device-timed leg, inputs resident in HBM: creates this rank's image(s) of `workload`, fills them on the device, runs `warmup`
+    untimed and EXACTLY `steps` timed chains between barriers (CUDA events on the launching stream), checks what the timed launches
+    wrote against the oracle.  Returns the numbers and the first `keep` images (the rest is destroyed)."""
+    import floor_b200
+    lib = floor_b200.lib()
+    desc, dim, t, sharded, cid = WORKLOADS[workload]
+    rdim, layer_id0, levels, alg_bytes = workload_geometry(workload, world, rank, layers_override)
+    # rotate over enough images that a step never finds its input (or a previous output) in the 126 MB L2: at least two, and
+    # at least 2 x L2 worth of them for the small workloads (C1: 46 images of 5.6 MB); a layered shard is far larger than L2
+    n_rot = 1 if sharded else int(min(64, max(2, -(-2 * L2_BYTES // alg_bytes))))
+    fill_ids = [layer_id0 if sharded else rank * n_rot + i for i in range(n_rot)]
+    rot = []
+    for i in range(n_rot):
+        im = ctx.create_image(q, rdim, t)
+        im.fill_synthetic(q, cid, fill_ids[i])
         rot.append(im)
     q.finish()
-    level0 = img.levels[0]["size"]
-    alg_bytes = img.image_data_size_mip_maps  # level 0 read once + levels >= 1 written once
-    texels_in = level0 // img.get_bytes_per_pixel()
+    img = rot[0]
+    assert img.image_data_size_mip_maps == alg_bytes and img.mip_level_count == levels
     plan = img.plan()
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_
-        torch.cuda.set_device(local_rank)
-        dist_.init_process_group("nccl")
-        dist = dist_
-
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-        q.finish()
-
-    # ---- resident (HBM -> HBM) timing ----
-    for i in range(max(args.warmup, min(n_rot, 8))):
+    for i in range(max(warmup, min(n_rot, 8))):
         rot[i % n_rot].enqueue_mip_map_chain(q)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    ranks.barrier(q)
+    if sampler is not None:
         sampler.start()
     launches0 = lib.flmip_launch_count()
-    barrier()
+    ranks.barrier(q)
     ev0 = q.record_event()
-    for i in range(args.steps):
+    for i in range(steps):
         rot[(i + 1) % n_rot].enqueue_mip_map_chain(q)
     ev1 = q.record_event()
     ms = q.elapsed_ms(ev0, ev1)
-    barrier()
+    ranks.barrier(q)
     launches = lib.flmip_launch_count() - launches0
     clocks = None
-    if rank == 0:
+    if sampler is not None:
         # nvidia-smi samples every 100 ms and needs as long to start, the timed region of most workloads lasts a few ms: keep the
         # same steps running (untimed) until the sampler has seen the GPU under this load for a few samples
         t_s = time.perf_counter()
@@ -206,7 +275,62 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop(settle=0.0)
         clocks["window"] = ("the timed region (%.1f ms) followed by %.0f ms of the same steps, untimed, so that the 100 ms sampler sees this load"
                             % (ms, (time.perf_counter() - t_s) * 1e3))
-    barrier()
+    ranks.barrier(q)
+    # what did the timed launches write?  image 1 % n_rot was the first one of the timed loop
+    chk_i = 1 % n_rot
+    pc = parity_check(rot[chk_i], q, workload, fill_ids[chk_i], sharded)
+    texels_in = img.levels[0]["size"] // img.get_bytes_per_pixel()
+    ms_all, = ranks.reduce([ms], "max")
+    total_bytes, total_texels, mism, checked = ranks.reduce([alg_bytes, texels_in, pc["mismatches"], pc["layers_checked"]], "sum")
+    pc = dict(pc, mismatches=int(mism), layers_checked=int(checked))
+    for im in rot[keep:]:
+        im.destroy()
+    ms_per_step = ms_all / steps
+    return {"images": rot[:keep], "fill_ids": fill_ids[:keep], "rdim": rdim, "alg_bytes": alg_bytes, "levels": levels, "plan": plan, "ms_rank": ms, "ms_per_step": ms_per_step,
+            "value": total_bytes / (ms_per_step * 1e-3) / 1e9, "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "total_bytes": total_bytes,
+            "mtexels_in_per_s": total_texels / (ms_per_step * 1e-3) / 1e6, "launches": int(launches), "clocks": clocks, "parity_check": pc, "n_rot": n_rot,
+            "kernel": ("flmip_fast%dd_k*" if plan["single_pass"] else "flmip_tile%dd_k*") % (3 if (t >> 16) & 3 == 3 else 2)}
+
+
+def pcie_probe(q, img, pin_in, pin_out, h2d, d2h, last, ranks, reps=6):
+    """the ceiling of the end-to-end leg: the same copies through the same C-ABI calls with no kernel between them -- upload alone,
+    read-back alone, and both directions at once (two queues), every rank at the same time (max over ranks)"""
+    def timed(fn, Qs):
+        fn(); [Q.finish() for Q in Qs]
+        ranks.barrier(q)
+        t0 = Qs[0].record_event()
+        for _ in range(reps):
+            fn()
+        ends = [Q.record_event() for Q in Qs]
+        ms = max(Qs[0].elapsed_ms(t0, e, destroy=False) for e in ends) / reps
+        [Q.finish() for Q in Qs]
+        ranks.barrier(q)
+        return ms
+    q2 = pin_out["queue"]
+    up = lambda: img.upload_levels(q, pin_in.ptr, 0, 0, sync=False, nbytes=h2d)
+    down = lambda: img.download_levels(q2, 1, last, out=pin_out["buf"].ptr, sync=False)
+    ms_up, ms_down = timed(up, [q]), timed(down, [q2])
+    ms_both = timed(lambda: (up(), down()), [q, q2])
+    ms_up, ms_down, ms_both = ranks.reduce([ms_up, ms_down, ms_both], "max")
+    return {"h2d_gbs": round(h2d / ms_up / 1e6, 2), "d2h_gbs": round(d2h / ms_down / 1e6, 2), "duplex_ms_per_step": round(ms_both, 4),
+            "note": "pinned host <-> device copies of one step's bytes through flmip_image_upload / _download, no kernel; per rank, all ranks at once, max over ranks"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import floor_b200
+    desc, dim, t, sharded, cid = WORKLOADS[args.workload]
+    ctx = floor_b200.device_context()
+    dev = ctx.get_device(local_rank)
+    q = ctx.create_queue(dev)
+    ranks = Ranks(world, local_rank)
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- resident (HBM -> HBM) timing of the headline workload ----
+    n_images = 2 if not sharded else 1  # images of the end-to-end leg (one queue each)
+    R = time_resident(ctx, dev, q, ranks, rank, world, args.workload, args.steps, args.warmup, args.layers, ClockSampler(local_rank) if rank == 0 else None,
+                      keep=n_images)
+    images, img = R["images"], R["images"][0]
+    alg_bytes, level0 = R["alg_bytes"], R["images"][0].levels[0]["size"]
 
     # ---- end to end through the public API with host buffers (pinned), H2D + chain + D2H every step ----
     e2e_steps = max(4, min(args.steps, 20))
@@ -215,8 +339,9 @@ def run_ours(args, rank, world, local_rank):
     h2d = level0
     d2h = alg_bytes - level0
     e2e_ms = e2e_blocking_ms = float("nan")
+    pcie = None
     if e2e_steps:
-        pin_in = floor_b200.pinned_buffer(h2d, local_rank)
+        pin_in = floor_b200.pinned_buffer(h2d, local_rank, write_combined=not args.no_write_combined)  # upload only: the CPU never reads it
         pin_out = [floor_b200.pinned_buffer(max(d2h, 1), local_rank) for _ in range(n_images)]
         images[0].download_levels(q, 0, 0, out=pin_in.ptr)  # synthetic level 0 back to the host staging buffer
         q.finish()
@@ -231,14 +356,14 @@ def run_ours(args, rank, world, local_rank):
 
         # (a) blocking, the reference's semantics: write -> chain -> read back, one image at a time
         e2e_enqueue(0); q.finish()
-        barrier()
+        ranks.barrier(q)
         t0 = q.record_event()
         for i in range(e2e_steps):
             e2e_enqueue(0)
             q.finish()
         t1 = q.record_event()
         e2e_blocking_ms = q.elapsed_ms(t0, t1) / e2e_steps
-        barrier()
+        ranks.barrier(q)
         # (b) the same steps through the non-blocking calls on one queue per image: the read-back of step k overlaps
         #     the upload of step k + 1 (PCIe is full duplex); every step still moves all of its bytes both ways
         t0 = q.record_event()
@@ -250,58 +375,68 @@ def run_ours(args, rank, world, local_rank):
         e2e_ms = max(Q.elapsed_ms(t0, e, destroy=False) for Q, e in zip(qs, ends)) / e2e_steps
         for Q in qs:
             Q.finish()
-        barrier()
+        ranks.barrier(q)
+        # the result that arrived on the host in the last step is the chain of the uploaded level 0: compare with the device copy
+        e2e_ok = bool(np.array_equal(pin_out[(e2e_steps - 1) % n_images].array[:d2h], images[(e2e_steps - 1) % n_images].download_levels(q, 1, last)))
+        # (c) the ceiling: the same copies without the kernel
+        pcie = pcie_probe(q, images[0], pin_in, {"queue": qs[-1] if n_images > 1 else ctx.create_queue(dev), "buf": pin_out[-1]}, h2d, d2h, last, ranks)
+        e2e_all, = ranks.reduce([e2e_ms], "max")
+    for im in images:
+        im.destroy()
 
-    # max over ranks of the device time
-    ms_all, e2e_all = ms, e2e_ms
-    if dist is not None:
-        import torch
-        tt = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_all, e2e_all = float(tt[0]), float(tt[1])
-        tb = torch.tensor([float(alg_bytes), float(texels_in)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-        total_bytes, total_texels = float(tb[0]), float(tb[1])
-    else:
-        total_bytes, total_texels = float(alg_bytes), float(texels_in)
-
-    ms_per_step = ms_all / args.steps
-    value = total_bytes / (ms_per_step * 1e-3) / 1e9
-    peak, peak_src = measured_peak_gbs()
-    achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9  # this rank's kernel: algorithmic bytes per launch / avg launch duration
+    # ---- BASELINE configs 3 and 4: layers / cubes sharded across the ranks (strong scaling), same timing rules ----
+    layered = None
+    if args.workload == "c2" and not args.no_layered:
+        layered = {}
+        for wl in ("c3", "c4"):
+            try:
+                L = time_resident(ctx, dev, q, ranks, rank, world, wl, max(3, min(args.steps, 10)), 3, keep=0)
+            except floor_b200.FlmipError as e:
+                layered[wl] = {"unavailable": str(e)[:200]}
+                continue
+            layered[wl] = {"workload": WORKLOADS[wl][0], "value": round(L["value"], 2), "unit": "GB/s", "ms_per_step": round(L["ms_per_step"], 5),
+                           "steps": max(3, min(args.steps, 10)), "scaling": "strong", "layers_per_gpu": L["rdim"][2] * (6 if wl == "c4" else 1),
+                           "algorithmic_bytes_per_gpu_step": L["alg_bytes"], "per_gpu_achieved": round(L["achieved"], 2), "frac": round(L["achieved"] / peak, 4),
+                           "launches_per_step": L["plan"]["launches"], "kernel": L["kernel"], "parity_check": L["parity_check"],
+                           "limiter": "fixed per-launch cost (launch + ring ramp-up + last-CTA tail of the group / layer stages), paid once per step whatever the shard size"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu(args.workload, steps=None, warmup=0)
 
     if rank == 0:
+        plan = R["plan"]
+        e2e = None
+        if e2e_steps:
+            e2e_value = R["total_bytes"] / (e2e_all * 1e-3) / 1e9
+            # ceiling of the pipelined leg: every step moves h2d bytes up and d2h bytes down; with full duplex the slower direction bounds it
+            ceil_ms = max(h2d / (pcie["h2d_gbs"] * 1e6), d2h / (pcie["d2h_gbs"] * 1e6))
+            pcie_peak = R["total_bytes"] / (ceil_ms * 1e-3) / 1e9
+            e2e = {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": round(e2e_all, 4), "steps": e2e_steps, "blocking_value": round(alg_bytes / (e2e_blocking_ms * 1e-3) / 1e9, 3),
+                   "blocking_ms_per_step": round(e2e_blocking_ms, 4), "result_on_host_matches_device": e2e_ok,
+                   "pcie_peak_gbs": round(pcie_peak, 3), "frac": round(e2e_value / pcie_peak, 4), "pcie": pcie,
+                   "upload_buffer": "pinned" + ("" if args.no_write_combined else ", write-combined"),
+                   "note": "per step: pinned host level 0 -> H2D -> chain -> D2H of all generated levels; value = non-blocking calls, one queue per image, so the read-back of step k overlaps the upload of step k+1; blocking_value = the reference's blocking semantics on one queue (this rank); pcie_peak_gbs = the same metric if the step cost only its slower copy direction at the bandwidth measured with no kernel (all ranks copying at once)"}
         out = {
-            "metric": "mip_chain_throughput", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+            "metric": "mip_chain_throughput", "value": round(R["value"], 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(R["ms_per_step"], 6), "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
-            "config": {"workload": desc + (f"; one such image per GPU ({world} independent textures)" if not sharded and world > 1 else ""),
-                       "levels": img.mip_level_count, "algorithmic_bytes_per_gpu_step": alg_bytes, "mtexels_in_per_s": round(total_texels / (ms_per_step * 1e-3) / 1e6, 1),
-                       "single_pass": plan["single_pass"], "launches_per_step": plan["launches"],
-                       "l2": ("working set per step (%.0f MB) exceeds the 126 MB L2" % (alg_bytes / 1e6) if alg_bytes > L2_BYTES else
-                              "inputs rotate over %d images (%.0f MB in total, more than twice the 126 MB L2)" % (n_rot, n_rot * alg_bytes / 1e6))
-                             + ("; steps rotate over %d images" % n_rot if n_rot > 1 and alg_bytes > L2_BYTES else ""),
-                       "parallelism": "independent images per GPU, no collective" if not sharded else "contiguous layer ranges per GPU, no collective"},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src,
-                         "kernel": ("flmip_fast%dd_*" if plan["single_pass"] else "flmip_tile%dd_*") % (3 if (t >> 16) & 3 == 3 else 2), "algorithmic_bytes_per_launch": alg_bytes},
-            "e2e": None if not e2e_steps else {"value": round(total_bytes / (e2e_all * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": round(e2e_all, 4), "steps": e2e_steps, "blocking_value": round(alg_bytes / (e2e_blocking_ms * 1e-3) / 1e9, 3), "blocking_ms_per_step": round(e2e_blocking_ms, 4),
-                    "note": "per step: pinned host level 0 -> H2D -> chain -> D2H of all generated levels; value = non-blocking calls, one queue per image, so the read-back of step k overlaps the upload of step k+1; blocking_value = the reference's blocking semantics on one queue (this rank)"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "config": config_for(args.workload, world, args.layers),
+            "detail": {"mtexels_in_per_s": round(R["mtexels_in_per_s"], 1), "single_pass": plan["single_pass"], "launches_per_step": plan["launches"],
+                       "images_in_rotation": R["n_rot"]},
+            "roofline": {"bound": "hbm", "achieved": round(R["achieved"], 2), "peak": peak, "unit": "GB/s", "frac": round(R["achieved"] / peak, 4),
+                         "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src, "kernel": R["kernel"], "algorithmic_bytes_per_launch": alg_bytes},
+            "parity_check": R["parity_check"],
+            "layered": layered,
+            "e2e": e2e,
+            "gpu_launches": R["launches"],
+            "clocks": R["clocks"],
             "cpu_baseline": cpu_baseline,
             "device": dev.name,
         }
         print(json.dumps(out), flush=True)
-    for im in rot:
-        im.destroy()
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def run_cpu(workload: str, steps: int, warmup: int):
@@ -355,12 +490,14 @@ def run_cpu(workload: str, steps: int, warmup: int):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    base = run_cpu(args.workload, steps=args.steps, warmup=min(args.warmup, 1))
-    desc = WORKLOADS[args.workload][0]
+    base = run_cpu(args.workload, steps=args.steps, warmup=args.warmup)
     out = {"impl": "reference", "metric": "mip_chain_throughput", "value": base["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-           "warmup": min(args.warmup, 1), "ms_per_step": round(base["seconds_per_step"] * 1e3, 3), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
-           "config": {"workload": desc, "note": "CPU arm on the host cores: " + ("the reference's own Host-Compute kernels (oracle/_ref)" if base["kind"] == "reference" else "Host-Compute restatement (oracle/_ref absent)")},
+           "warmup": args.warmup, "ms_per_step": round(base["seconds_per_step"] * 1e3, 3), "higher_is_better": True,
+           "scaling": "strong" if WORKLOADS[args.workload][3] else "weak", "vs_baseline": None, "dtype": DTYPE[args.workload],
+           "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
+           "config": config_for(args.workload, world, args.layers),
+           "detail": {"arm": "CPU arm on the host cores: " + ("the reference's own Host-Compute kernels (oracle/_ref)" if base["kind"] == "reference" else "Host-Compute restatement (oracle/_ref absent)"),
+                      "sample": base["sample"]},
            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -376,8 +513,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="tuning runs only: override the layer / cube count of c3 / c4")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
+    ap.add_argument("--no-layered", action="store_true", help="tuning runs only: skip the sharded C3 / C4 legs of the default line")
+    ap.add_argument("--no-write-combined", action="store_true", help="A/B: plain pinned upload buffer instead of a write-combined one")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

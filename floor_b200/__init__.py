@@ -20,13 +20,15 @@ CSRC = os.path.join(_HERE, "csrc")
 FLMIP_OK = 0
 ERR_NO_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_DRIVER, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
 IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED = 1, 2, 4, 8, 16
+HOST_WRITE_COMBINED = 1
 
 # every symbol include/floor_b200_mip.h declares (checked by tests/test_cabi.py without a GPU)
 EXPORTS = [
     "flmip_init", "flmip_device_count", "flmip_get_device_info", "flmip_last_error_string", "flmip_launch_count",
     "flmip_stream_create", "flmip_stream_destroy", "flmip_stream_sync",
     "flmip_event_create", "flmip_event_record", "flmip_event_sync", "flmip_event_elapsed_ms", "flmip_event_destroy",
-    "flmip_host_alloc", "flmip_host_free",
+    "flmip_host_alloc", "flmip_host_alloc_ex", "flmip_host_free",
+    "flmip_device_attach_context", "flmip_image_create_external", "flmip_image_download_layers",
     "flmip_image_create", "flmip_image_destroy", "flmip_image_mip_level_count", "flmip_image_layer_count",
     "flmip_image_data_size", "flmip_image_get_level_info", "flmip_image_device_ptr", "flmip_image_plan",
     "flmip_image_upload", "flmip_image_download", "flmip_image_write", "flmip_image_zero",
@@ -47,7 +49,8 @@ class DeviceInfo(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 128), ("global_mem_size", ctypes.c_uint64), ("sm_major", ctypes.c_uint32),
                 ("sm_minor", ctypes.c_uint32), ("units", ctypes.c_uint32), ("max_total_local_size", ctypes.c_uint32),
                 ("max_image_2d_dim", ctypes.c_uint32 * 2), ("max_image_3d_dim", ctypes.c_uint32 * 3),
-                ("max_mip_levels", ctypes.c_uint32), ("driver_version", ctypes.c_uint32)]
+                ("max_mip_levels", ctypes.c_uint32), ("driver_version", ctypes.c_uint32), ("clock_mhz", ctypes.c_uint32),
+                ("mem_clock_mhz", ctypes.c_uint32), ("mem_bus_width", ctypes.c_uint32), ("l2_cache_size", ctypes.c_uint32)]
 
 
 class LevelInfo(ctypes.Structure):
@@ -98,6 +101,10 @@ def lib() -> ctypes.CDLL:
         "flmip_event_destroy": (i32, [i32, vp]),
         "flmip_host_alloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),
         "flmip_host_free": (i32, [i32, vp]),
+        "flmip_host_alloc_ex": (i32, [i32, ctypes.c_size_t, u32, ctypes.POINTER(vp)]),
+        "flmip_device_attach_context": (i32, [i32, vp]),
+        "flmip_image_create_external": (i32, [i32, u64, u32p, u32, u32, u64, u64, ctypes.POINTER(vp)]),
+        "flmip_image_download_layers": (i32, [vp, vp, ctypes.c_size_t, u32, u32, u32, u32, vp]),
         "flmip_image_create": (i32, [i32, u64, u32p, u32, u32, ctypes.POINTER(vp)]),
         "flmip_image_destroy": (i32, [vp]),
         "flmip_image_mip_level_count": (i32, [vp, u32p]),

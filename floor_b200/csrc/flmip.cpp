@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "mip_params.h"
@@ -53,7 +54,7 @@ int fail(int code, const char* fmt, ...) {
 	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
 	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuLaunchKernelEx) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
 	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy) F(cuGraphCreate) F(cuGraphAddKernelNode)           \
-	F(cuGraphInstantiate) F(cuGraphLaunch) F(cuGraphExecDestroy) F(cuGraphDestroy)
+	F(cuGraphInstantiate) F(cuGraphLaunch) F(cuGraphExecDestroy) F(cuGraphDestroy) F(cuStreamWaitEvent) F(cuCtxGetDevice)
 
 struct driver_api {
 #define FL_DECL(name) decltype(&name) p_##name = nullptr;
@@ -71,6 +72,10 @@ struct device_state {
 	std::unordered_map<std::string, CUfunction> functions;
 	flmip_device_info info {};
 	uint32_t smem_per_sm = 0, smem_per_block_optin = 0;
+	bool ctx_attached = false;      // the context was handed in by flmip_device_attach_context (not retained, never released)
+	CUstream util_stream = nullptr; // private non-blocking stream for creation-time memsets (never the legacy stream)
+	std::mutex images_mtx;
+	std::unordered_set<flmip_image_s*> images; // live images of this device (flmip_stream_destroy hands their chains over)
 };
 
 std::once_flag init_once;
@@ -149,6 +154,10 @@ void do_init() {
 		ds->smem_per_sm = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_MULTIPROCESSOR);
 		ds->smem_per_block_optin = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN);
 		ds->info.driver_version = (uint32_t)version;
+		ds->info.clock_mhz = attr(CU_DEVICE_ATTRIBUTE_CLOCK_RATE) / 1000u;
+		ds->info.mem_clock_mhz = attr(CU_DEVICE_ATTRIBUTE_MEMORY_CLOCK_RATE) / 1000u;
+		ds->info.mem_bus_width = attr(CU_DEVICE_ATTRIBUTE_GLOBAL_MEMORY_BUS_WIDTH);
+		ds->info.l2_cache_size = attr(CU_DEVICE_ATTRIBUTE_L2_CACHE_SIZE);
 		devices.push_back(ds);
 	}
 	init_status = FLMIP_OK;
@@ -321,6 +330,15 @@ struct flmip_image_s {
 	// levels the single-pass launch does not produce: multi-level tile kernel (2D / 3D) or one generic launch per level
 	bool tiled = false;
 	std::string tile_name;
+	bool external_mem = false; // `mem` belongs to the caller (flmip_image_create_external): never freed here
+	// One chain per image may be in flight at a time: the group / layer / scheduler counters beside the image are shared by every
+	// launch on it.  Chains on ONE stream are ordered by the stream; when a chain is enqueued on a different stream than the
+	// previous one, that stream is first made to wait for everything enqueued on the old stream so far (event hand-over), so
+	// overlapping chains on one image serialise instead of corrupting each other.
+	std::mutex gen_mtx;
+	CUstream last_stream = nullptr;
+	bool has_last = false, pending_handover = false;
+	CUevent handover = nullptr;
 };
 
 namespace {
@@ -390,6 +408,11 @@ bool next_level_has_texels(const flmip_image_s& im, uint32_t lvl) {
 	if (n >= im.level_count) return false;
 	const flmip_level_info& li = im.levels[n];
 	return li.dim[0] != 0 && (im.dc < 2 || li.dim[1] != 0) && (im.dc < 3 || li.dim[2] != 0);
+}
+
+uint32_t env_u32(const char* name, uint32_t def) {
+	const char* v = getenv(name);
+	return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : def;
 }
 
 // decides whether the single-pass kernel applies and how far it gets; mirrors fast_body() in mip_kernels.cu
@@ -476,8 +499,12 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	const uint64_t n_counters = n_groups + im.layers + 2u /* scheduler */;
 #endif
 	CU_TRY(cu.p_cuMemAlloc(&im.counters, n_counters * sizeof(uint32_t)), "cuMemAlloc(counters)");
-	CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, nullptr), "cuMemsetD32Async(counters)");
-	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
+	{
+		std::lock_guard<std::mutex> lock(ds->mtx);
+		if (!ds->util_stream) CU_TRY(cu.p_cuStreamCreate(&ds->util_stream, CU_STREAM_NON_BLOCKING), "cuStreamCreate(util)");
+		CU_TRY(cu.p_cuMemsetD32Async(im.counters, 0, n_counters, ds->util_stream), "cuMemsetD32Async(counters)");
+		CU_TRY(cu.p_cuStreamSynchronize(ds->util_stream), "cuStreamSynchronize(util)");
+	}
 	P.counters = im.counters;
 	P.sched = im.counters + (n_groups + im.layers) * sizeof(uint32_t);
 
@@ -495,17 +522,15 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	// persistent launch shape: CTAs per SM x ring depth that fit the SM's shared memory (1 KiB is reserved per CTA).
 	// Defaults: 2 CTAs per SM x 2 stages (128 KiB of loads in flight per SM: more only adds queueing latency to every
 	// fence / atomic round trip of the finishers); FLMIP_CTAS_PER_SM / FLMIP_STAGES override for tuning.
-	auto env_u32 = [](const char* name, uint32_t def) {
-		const char* v = getenv(name);
-		return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : def;
-	};
-	uint32_t ctas_per_sm = env_u32("FLMIP_CTAS_PER_SM", 2);
+	// (the overrides are read once per process)
+	static const uint32_t env_ctas_per_sm = env_u32("FLMIP_CTAS_PER_SM", 2), env_stages = env_u32("FLMIP_STAGES", 2);
+	uint32_t ctas_per_sm = env_ctas_per_sm;
 	if (ctas_per_sm < 1) ctas_per_sm = 1;
 	const uint32_t per_cta = ds->smem_per_sm / ctas_per_sm - 1024u - 2048u /* static: mbarriers, ticket, lock, unit patches */;
 	const uint32_t budget = per_cta < ds->smem_per_block_optin - 2048u ? per_cta : ds->smem_per_block_optin - 2048u;
 	if (budget < tl.cascade_smem_bytes + tl.tile_bytes) return fail(FLMIP_ERR_INVALID, "FLMIP_CTAS_PER_SM=%u leaves no room for a tile", ctas_per_sm);
 	uint32_t stages = (budget - tl.cascade_smem_bytes) / tl.tile_bytes;
-	const uint32_t want = env_u32("FLMIP_STAGES", 2);
+	const uint32_t want = env_stages;
 	if (stages > want) stages = want;
 	if (stages > FLMIP_MAX_STAGES) stages = FLMIP_MAX_STAGES;
 	if (stages < 1) stages = 1;
@@ -681,6 +706,18 @@ int flmip_stream_create(int device, flmip_stream* out) {
 }
 int flmip_stream_destroy(int device, flmip_stream stream) {
 	WITH_DEVICE(device)
+	{
+		// images whose last chain was enqueued on this stream: leave an event behind that the next chain on them waits for
+		std::lock_guard<std::mutex> lock(ds->images_mtx);
+		for (flmip_image_s* im : ds->images) {
+			std::lock_guard<std::mutex> g(im->gen_mtx);
+			if (!im->has_last || im->last_stream != (CUstream)stream) continue;
+			if (!im->handover && cu.p_cuEventCreate(&im->handover, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) continue;
+			if (cu.p_cuEventRecord(im->handover, (CUstream)stream) == CUDA_SUCCESS) im->pending_handover = true;
+			im->has_last = false;
+			im->last_stream = nullptr;
+		}
+	}
 	CU_TRY(cu.p_cuStreamDestroy((CUstream)stream), "cuStreamDestroy");
 	return FLMIP_OK;
 }
@@ -724,13 +761,25 @@ int flmip_host_alloc(int device, size_t size, void** out) {
 	CU_TRY(cu.p_cuMemHostAlloc(out, size, CU_MEMHOSTALLOC_PORTABLE), "cuMemHostAlloc");
 	return FLMIP_OK;
 }
+int flmip_host_alloc_ex(int device, size_t size, uint32_t flags, void** out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	WITH_DEVICE(device)
+	unsigned f = CU_MEMHOSTALLOC_PORTABLE;
+	if (flags & FLMIP_HOST_WRITE_COMBINED) f |= CU_MEMHOSTALLOC_WRITECOMBINED;
+	CU_TRY(cu.p_cuMemHostAlloc(out, size, f), "cuMemHostAlloc");
+	return FLMIP_OK;
+}
 int flmip_host_free(int device, void* ptr) {
 	WITH_DEVICE(device)
 	CU_TRY(cu.p_cuMemFreeHost(ptr), "cuMemFreeHost");
 	return FLMIP_OK;
 }
 
-int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags, flmip_image* out) {
+} // extern "C"
+
+namespace {
+int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags, uint64_t external_ptr,
+					  uint64_t external_size, bool external, flmip_image* out) {
 	if (!out || !image_dim) return fail(FLMIP_ERR_INVALID, "null argument");
 	*out = nullptr;
 	auto im = new flmip_image_s;
@@ -779,9 +828,29 @@ int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim
 	ctx_guard guard;
 	rc = guard.push(ds);
 	if (rc != FLMIP_OK) { delete im; return rc; }
-	CUresult r = cu.p_cuMemAlloc(&im->mem, im->total_size);
-	if (r != CUDA_SUCCESS) { delete im; return cu_fail(r, "cuMemAlloc(image)"); }
+	if (external) {
+		// caller-owned linear memory in floor's host layout (another context's buffer, an imported Vulkan / OpenCL allocation ...)
+		if (external_ptr == 0 || external_size < im->total_size) {
+			const unsigned long long need = im->total_size;
+			delete im;
+			return fail(FLMIP_ERR_INVALID, "external image memory: null or smaller than the %llu bytes of the level-major image", need);
+		}
+		if (external_ptr & 15u) { delete im; return fail(FLMIP_ERR_INVALID, "external image memory must be 16-byte aligned (TMA, vector stores)"); }
+		im->mem = (CUdeviceptr)external_ptr;
+		im->external_mem = true;
+	} else {
+		CUresult r = cu.p_cuMemAlloc(&im->mem, im->total_size);
+		if (r != CUDA_SUCCESS) { delete im; return cu_fail(r, "cuMemAlloc(image)"); }
+	}
 	rc = plan_fast(*im, ds, (flags & FLMIP_IMAGE_FORCE_TILED) ? (flags | FLMIP_IMAGE_FORCE_GENERIC) : flags);
+	if (rc != FLMIP_OK && rc != FLMIP_ERR_OUT_OF_MEMORY) {
+		// the single-pass plan is an optimisation: when one of its optional steps fails (tensor-map encoding, the shared-memory
+		// opt-in, a tuning override that leaves no room for a tile) the tile / literal kernels still serve the image
+		if (im->counters) cu.p_cuMemFree(im->counters);
+		im->counters = 0;
+		im->fast = false;
+		rc = FLMIP_OK;
+	}
 	if (rc == FLMIP_OK && im->dc >= 2 && ((flags & FLMIP_IMAGE_FORCE_TILED) || !(flags & FLMIP_IMAGE_FORCE_GENERIC))) {
 		char name[64];
 		snprintf(name, sizeof(name), "flmip_tile%ud_k%u_c%u", im->dc, im->elem_kind, im->channels);
@@ -794,19 +863,80 @@ int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim
 	}
 	if (rc != FLMIP_OK) {
 		if (im->counters) cu.p_cuMemFree(im->counters);
-		cu.p_cuMemFree(im->mem);
+		if (!im->external_mem) cu.p_cuMemFree(im->mem);
 		delete im;
 		return rc;
 	}
+	{
+		std::lock_guard<std::mutex> lock(ds->images_mtx);
+		ds->images.insert(im);
+	}
 	*out = im;
+	return FLMIP_OK;
+}
+
+// Orders a chain about to be enqueued on `stream` after the previous chain of the image (see flmip_image_s::gen_mtx).  Called with
+// gen_mtx held and the device's context current.
+int order_after_previous_chain(flmip_image_s& im, CUstream stream) {
+	if (tl_recorder) return FLMIP_OK; // recording a batch graph: flmip_batch_generate orders the graph launch
+	if (im.pending_handover) {
+		CU_TRY(cu.p_cuStreamWaitEvent(stream, im.handover, 0), "cuStreamWaitEvent(chain hand-over)");
+		im.pending_handover = false;
+	} else if (im.has_last && im.last_stream != stream) {
+		if (!im.handover) CU_TRY(cu.p_cuEventCreate(&im.handover, CU_EVENT_DISABLE_TIMING), "cuEventCreate(chain hand-over)");
+		CU_TRY(cu.p_cuEventRecord(im.handover, im.last_stream), "cuEventRecord(chain hand-over)");
+		CU_TRY(cu.p_cuStreamWaitEvent(stream, im.handover, 0), "cuStreamWaitEvent(chain hand-over)");
+	}
+	im.last_stream = stream;
+	im.has_last = true;
+	return FLMIP_OK;
+}
+} // namespace
+
+extern "C" {
+
+int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags, flmip_image* out) {
+	return create_image_impl(device, image_type, image_dim, mip_level_limit, flags, 0, 0, false, out);
+}
+
+int flmip_image_create_external(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags,
+								uint64_t device_ptr, uint64_t size, flmip_image* out) {
+	return create_image_impl(device, image_type, image_dim, mip_level_limit, flags, device_ptr, size, true, out);
+}
+
+int flmip_device_attach_context(int device, void* cu_context) {
+	if (!cu_context) return fail(FLMIP_ERR_INVALID, "null context");
+	const int rc = ensure_init();
+	if (rc != FLMIP_OK) return rc;
+	if (device < 0 || (size_t)device >= devices.size()) return fail(FLMIP_ERR_INVALID, "invalid device index %d (have %zu)", device, devices.size());
+	device_state* ds = devices[(size_t)device];
+	std::lock_guard<std::mutex> lock(ds->mtx);
+	const CUcontext cur = ds->ctx.load(std::memory_order_acquire);
+	if (cur == (CUcontext)cu_context) return FLMIP_OK;
+	if (cur) return fail(FLMIP_ERR_INVALID, "device %d already runs on another context: attach before the first use of the device", device);
+	// the context must belong to this device
+	CU_TRY(cu.p_cuCtxPushCurrent((CUcontext)cu_context), "cuCtxPushCurrent(attached context)");
+	CUdevice d = -1;
+	const CUresult r = cu.p_cuCtxGetDevice(&d);
+	CUcontext old = nullptr;
+	cu.p_cuCtxPopCurrent(&old);
+	if (r != CUDA_SUCCESS) return cu_fail(r, "cuCtxGetDevice");
+	if (d != ds->dev) return fail(FLMIP_ERR_INVALID, "the context belongs to another device");
+	ds->ctx_attached = true;
+	ds->ctx.store((CUcontext)cu_context, std::memory_order_release);
 	return FLMIP_OK;
 }
 
 int flmip_image_destroy(flmip_image img) {
 	if (!img) return FLMIP_OK;
 	WITH_DEVICE(img->device)
+	{
+		std::lock_guard<std::mutex> lock(ds->images_mtx);
+		ds->images.erase(img);
+	}
+	if (img->handover) cu.p_cuEventDestroy(img->handover);
 	if (img->counters) cu.p_cuMemFree(img->counters);
-	if (img->mem) cu.p_cuMemFree(img->mem);
+	if (img->mem && !img->external_mem) cu.p_cuMemFree(img->mem);
 	delete img;
 	return FLMIP_OK;
 }
@@ -880,6 +1010,28 @@ int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t l
 	return FLMIP_OK;
 }
 
+int flmip_image_download_layers(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, uint32_t layer_first,
+								uint32_t layer_count, flmip_stream stream) {
+	if (check_image(img)) return FLMIP_ERR_INVALID;
+	if (!dst) return fail(FLMIP_ERR_INVALID, "null destination");
+	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
+	if (layer_count == 0 || (uint64_t)layer_first + layer_count > img->layers)
+		return fail(FLMIP_ERR_INVALID, "invalid layer range [%u, +%u) of %u layers", layer_first, layer_count, img->layers);
+	uint64_t need = 0;
+	for (uint32_t l = level_first; l <= level_last; ++l) need += img->levels[l].slice_size * layer_count;
+	if (dst_size < need) return fail(FLMIP_ERR_INVALID, "image download: insufficient host buffer (%zu < %llu)", dst_size, (unsigned long long)need);
+	WITH_DEVICE(img->device)
+	uint8_t* cur = static_cast<uint8_t*>(dst);
+	for (uint32_t l = level_first; l <= level_last; ++l) {
+		const flmip_level_info& li = img->levels[l];
+		const uint64_t bytes = li.slice_size * layer_count;
+		if (bytes == 0) continue;
+		CU_TRY(cu.p_cuMemcpyDtoHAsync(cur, img->mem + li.offset + (uint64_t)layer_first * li.slice_size, bytes, (CUstream)stream), "cuMemcpyDtoHAsync(layers)");
+		cur += bytes;
+	}
+	return FLMIP_OK;
+}
+
 int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
 					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream) {
 	if (check_image(img)) return FLMIP_ERR_INVALID;
@@ -890,8 +1042,27 @@ int flmip_image_write(flmip_image img, const void* src, size_t src_size, const u
 	for (uint32_t d = 0; d < img->dc; ++d) {
 		if (extent[d] == 0 || (uint64_t)offset[d] + extent[d] > img->dim[d]) return fail(FLMIP_ERR_INVALID, "image write: offset + extent out of bounds in dim %u", d);
 	}
-	WITH_DEVICE(img->device)
+	if (src_size == 0) return fail(FLMIP_ERR_INVALID, "image write: trying to write 0 bytes");
+	// The per-level region (offset >> level, max(extent >> level, 1)) can leave a level whose dim is odd (dim 5, offset 4, extent 1:
+	// level 1 has 2 texels, the region starts at 2).  The reference's cuMemcpy3D into the level's CUarray fails there and write()
+	// returns false; on linear memory nothing would stop the copy from running into the next level, so every level of the range
+	// is checked before the first copy is issued (nothing is written when the call fails).
 	const uint32_t n_layers = layer_range[1] - layer_range[0] + 1u;
+	uint64_t need = 0;
+	for (uint32_t level = mip_level_range[0]; level <= mip_level_range[1]; ++level) {
+		const flmip_level_info& li = img->levels[level];
+		if (li.size == 0) continue;
+		uint64_t texels = 1;
+		for (uint32_t d = 0; d < img->dc; ++d) {
+			const uint32_t o = offset[d] >> level, e = (extent[d] >> level) ? (extent[d] >> level) : 1u;
+			if ((uint64_t)o + e > li.dim[d])
+				return fail(FLMIP_ERR_INVALID, "image write: region [%u, +%u) leaves mip-level %u (%u texels) in dim %u", o, e, level, li.dim[d], d);
+			texels *= e;
+		}
+		need += texels * img->bpp * n_layers;
+	}
+	if (src_size < need) return fail(FLMIP_ERR_INVALID, "image write: insufficient host data (%zu < %llu)", src_size, (unsigned long long)need);
+	WITH_DEVICE(img->device)
 	const uint8_t* cur = static_cast<const uint8_t*>(src);
 	size_t left = src_size;
 	for (uint32_t level = mip_level_range[0]; level <= mip_level_range[1]; ++level) {
@@ -1065,8 +1236,14 @@ int flmip_tiled_download(flmip_image geometry, void* mipmapped_array, void* dst,
 
 int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream) {
 	if (check_image(img)) return FLMIP_ERR_INVALID;
-	if (img->level_count < 2 || first_level + 1 >= img->level_count) return FLMIP_OK; // nothing to generate
+	if (first_level >= img->level_count) return fail(FLMIP_ERR_INVALID, "mip level %u out of range (%u levels)", first_level, img->level_count);
+	if (first_level + 1 == img->level_count) return FLMIP_OK; // nothing to generate
 	WITH_DEVICE(img->device)
+	std::lock_guard<std::mutex> gen_lock(img->gen_mtx);
+	{
+		const int rc = order_after_previous_chain(*img, (CUstream)stream);
+		if (rc != FLMIP_OK) return rc;
+	}
 	uint32_t next = first_level + 1; // first level still to be produced
 	if (img->fast && first_level == 0) {
 		CUfunction fn = nullptr;
@@ -1099,6 +1276,7 @@ struct flmip_batch_s {
 	CUgraph graph = nullptr;
 	CUgraphExec exec = nullptr;
 	uint32_t nodes = 0, images = 0;
+	std::vector<flmip_image> members;
 };
 
 int flmip_batch_create(const flmip_image* images, uint32_t count, flmip_batch* out) {
@@ -1135,6 +1313,7 @@ int flmip_batch_create(const flmip_image* images, uint32_t count, flmip_batch* o
 	b->exec = exec;
 	b->nodes = rec.nodes;
 	b->images = count;
+	b->members.assign(images, images + count);
 	*out = b;
 	return FLMIP_OK;
 }
@@ -1143,6 +1322,11 @@ int flmip_batch_generate(flmip_batch batch, flmip_stream stream) {
 	if (!batch) return fail(FLMIP_ERR_INVALID, "null batch handle");
 	if (!batch->exec) return FLMIP_OK; // nothing to generate (single-level images)
 	WITH_DEVICE(batch->device)
+	for (flmip_image im : batch->members) { // the graph runs a chain on every member: same one-chain-per-image rule
+		std::lock_guard<std::mutex> g(im->gen_mtx);
+		const int rc = order_after_previous_chain(*im, (CUstream)stream);
+		if (rc != FLMIP_OK) return rc;
+	}
 	CU_TRY(cu.p_cuGraphLaunch(batch->exec, (CUstream)stream), "cuGraphLaunch");
 	launch_counter.fetch_add(batch->nodes, std::memory_order_relaxed);
 	return FLMIP_OK;

@@ -666,6 +666,7 @@ __device__ __forceinline__ bool arrive_last(uint32_t* counter, uint32_t expected
 		if (last) *counter = 0u;
 	}
 	last = __shfl_sync(0xFFFFFFFFu, last, 0);
+	__syncwarp(); // extends lane 0's acquire to the other lanes' later loads (shfl.sync alone orders no memory accesses)
 	return last != 0;
 }
 

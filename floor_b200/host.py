@@ -49,6 +49,10 @@ class device:
         self.max_mip_levels = info.max_mip_levels
         self.sm = (info.sm_major, info.sm_minor)
         self.driver_version = info.driver_version
+        self.clock = info.clock_mhz
+        self.mem_clock = info.mem_clock_mhz
+        self.mem_bus_width = info.mem_bus_width
+        self.l2_cache_size = info.l2_cache_size
         self.image_support = True
         self.image_mipmap_support = True
         self.image_mipmap_write_support = True
@@ -60,10 +64,11 @@ class device:
 class pinned_buffer:
     """page-locked host staging buffer exposed as a numpy uint8 array"""
 
-    def __init__(self, size: int, device_index: int = 0):
+    def __init__(self, size: int, device_index: int = 0, write_combined: bool = False):
+        from . import HOST_WRITE_COMBINED
         self._dev = device_index
         self._ptr = ctypes.c_void_p()
-        _check(_L().flmip_host_alloc(device_index, size, ctypes.byref(self._ptr)))
+        _check(_L().flmip_host_alloc_ex(device_index, size, HOST_WRITE_COMBINED if write_combined else 0, ctypes.byref(self._ptr)))
         self.size = size
         self.array = np.ctypeslib.as_array((ctypes.c_uint8 * size).from_address(self._ptr.value))
 
@@ -351,6 +356,16 @@ class device_image:
             cqueue.finish()
         return out
 
+    def download_layers(self, cqueue: device_queue, layer_first: int, layer_count: int = 1, level_first: int = 0, level_last: int | None = None) -> np.ndarray:
+        """layers [layer_first, +layer_count) of the given levels, laid out like an image of `layer_count` layers"""
+        if level_last is None:
+            level_last = self.mip_level_count - 1
+        n = sum(self.levels[l]["slice_size"] for l in range(level_first, level_last + 1)) * layer_count
+        out = np.empty(n, dtype=np.uint8)
+        _check(_L().flmip_image_download_layers(self._handle, out.ctypes.data, n, level_first, level_last, layer_first, layer_count, cqueue._stream))
+        cqueue.finish()
+        return out
+
     def fill_synthetic(self, cqueue: device_queue, config_id: int, layer_id0: int = 0):
         _check(_L().flmip_image_fill_synthetic(self._handle, config_id, layer_id0, cqueue._stream))
 
@@ -418,9 +433,20 @@ class device_context:
     def get_devices(self):
         return list(self.devices)
 
-    def get_device(self, index: int = 0) -> device:
-        """device::TYPE::GPU0 + index; falls back to any device like the reference"""
+    def get_device(self, index: int | str = 0) -> device:
+        """device::TYPE::GPU0 + index, or "FASTEST_GPU" / "FASTEST" / "ANY"; falls back to any device like the reference"""
+        if isinstance(index, str):
+            return self.fastest_gpu_device if index.upper().startswith("FASTEST") else self.devices[0]
         return self.devices[index] if 0 <= index < len(self.devices) else self.devices[0]
+
+    @property
+    def fastest_gpu_device(self) -> device:
+        """cuda_context.cpp:340-395: score = cores per SM (128 for sm_100) x units x clock; the first device wins ties"""
+        best = self.devices[0]
+        for d in self.devices[1:]:
+            if 128 * d.units * d.clock > 128 * best.units * best.clock:
+                best = d
+        return best
 
     def create_queue(self, dev: device) -> device_queue:
         return device_queue(dev)

@@ -120,3 +120,34 @@ def bits_per_channel(t: int) -> int:
 
 def bytes_per_pixel(t: int) -> int:
     return (bits_per_channel(t) * channel_count(t) + 7) // 8
+
+
+def layer_count(dim, t: int) -> int:
+    """image_layer_count (image_types.hpp:716-726): dim = (w, h, d or layers, layers-for-3D); 6 faces per cube"""
+    d = list(dim) + [0] * (4 - len(dim))
+    n = 1
+    if t & IMAGE_TYPE.FLAG_ARRAY:
+        n = d[1] if dim_count(t) == 1 else (d[2] if dim_count(t) == 2 else d[3])
+    return n * 6 if t & IMAGE_TYPE.FLAG_CUBE else n
+
+
+def mip_level_count(dim, t: int, mip_level_limit: int = 0) -> int:
+    """image_mip_level_count (image_types.hpp:694-712) capped by mip_level_limit (device_image.hpp:483-485)"""
+    if not (t & IMAGE_TYPE.FLAG_MIPMAPPED):
+        return 1
+    m = max(list(dim)[: dim_count(t)])
+    n = max(m.bit_length(), 1)
+    return min(n, mip_level_limit) if mip_level_limit > 0 else n
+
+
+def level_size(dim, t: int, level: int) -> int:
+    """bytes of one level over all layers; level dims are dim >> level without max(1) (image_types.hpp:751-766)"""
+    texels = 1
+    for d in list(dim)[: dim_count(t)]:
+        texels *= d >> level
+    return texels * bytes_per_pixel(t) * layer_count(dim, t)
+
+
+def image_data_size(dim, t: int, mip_level_limit: int = 0) -> int:
+    """image_data_size_from_types over all levels (image_types.hpp:731-769)"""
+    return sum(level_size(dim, t, l) for l in range(mip_level_count(dim, t, mip_level_limit)))

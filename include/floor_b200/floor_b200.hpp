@@ -41,6 +41,17 @@ enum class DEVICE_CONTEXT_FLAGS : uint32_t { NONE = 0u };
 
 class device_context;
 class device_queue;
+class device_image;
+
+//! What device_image::generate_mip_map_chain dispatches to.  The reference keeps one `minify_program` per device_context
+//! (device_image.hpp:377-395) that provide_minify_program() fills from a compiled device_program (device_image.cpp:155-194); here a
+//! program is an object that generates levels > first_level of an image on a queue (enqueue only -- the caller blocks).  The
+//! built-in one launches the sm_100a kernels of libfloor_b200_mip.so; a context can register its own with
+//! device_image::provide_minify_program (e.g. to trace, or to route some image types elsewhere) -- no FUBAR, no toolchain.
+struct minify_program {
+	virtual ~minify_program() = default;
+	virtual bool minify(device_image& img, const device_queue& cqueue, uint32_t first_level) = 0;
+};
 
 //! fl::device: plain struct of public fields; the ones this path reads or a caller inspects
 struct device {
@@ -54,6 +65,7 @@ struct device {
 	TYPE type { TYPE::NONE };
 	std::string name;
 	uint32_t units { 0 };
+	uint32_t clock { 0 }, mem_clock { 0 }, mem_bus_width { 0 }; //!< MHz, MHz, bits (device.hpp:101-109)
 	uint64_t global_mem_size { 0 };
 	uint32_t max_total_local_size { 0 };
 	uint2 max_image_2d_dim;
@@ -181,7 +193,7 @@ public:
 	//! generates the whole mip chain from level 0; blocks until the last level has been written
 	virtual void generate_mip_map_chain(const device_queue& cqueue) {
 		if (!handle) return;
-		if (flmip_mip_chain_generate(handle, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) {
+		if (!generate_mip_map_chain_async(cqueue, 0u)) {
 			FLB_LOG_ERROR("mip-map minification failed: %s", flmip_last_error_string()); // device_image.cpp:250-253, 280-283: log + return
 			return;
 		}
@@ -189,7 +201,34 @@ public:
 	}
 	//! non-blocking variant (no equivalent in the reference): enqueue only; levels > first_level are regenerated
 	bool generate_mip_map_chain_async(const device_queue& cqueue, uint32_t first_level = 0u) {
-		return handle && flmip_mip_chain_generate_from(handle, first_level, const_cast<void*>(cqueue.get_queue_ptr())) == FLMIP_OK;
+		if (!handle) return false;
+		if (auto prog = lookup_minify_program(dev.context)) return prog->minify(*this, cqueue, first_level); // device_image.cpp:259-284
+		return flmip_mip_chain_generate_from(handle, first_level, const_cast<void*>(cqueue.get_queue_ptr())) == FLMIP_OK;
+	}
+
+	//! device_image::provide_minify_program (device_image.hpp:171-172, device_image.cpp:155-194): registers `prog` as the minify
+	//! program of `ctx`; every image of that context dispatches generate_mip_map_chain to it from now on.  nullptr restores the
+	//! built-in program.  Thread-safe (the reference guards its map with minify_programs_mtx, device_image.cpp:40).
+	static bool provide_minify_program(device_context& ctx, std::shared_ptr<minify_program> prog) {
+		std::lock_guard<std::mutex> lock(minify_programs_mtx());
+		if (prog) minify_programs()[&ctx] = std::move(prog);
+		else minify_programs().erase(&ctx);
+		return true;
+	}
+	//! device_image::destroy_minify_programs (device_image.cpp:549-552)
+	static void destroy_minify_programs() {
+		std::lock_guard<std::mutex> lock(minify_programs_mtx());
+		minify_programs().clear();
+	}
+	//! the built-in program: the single-pass / tile kernels of libfloor_b200_mip.so on the image's native handle
+	static std::shared_ptr<minify_program> builtin_minify_program() {
+		struct builtin : minify_program {
+			bool minify(device_image& img, const device_queue& cqueue, uint32_t first_level) override {
+				return flmip_mip_chain_generate_from(img.get_native_handle(), first_level, const_cast<void*>(cqueue.get_queue_ptr())) == FLMIP_OK;
+			}
+		};
+		static const auto prog = std::make_shared<builtin>();
+		return prog;
 	}
 
 	// ---- host <-> device ---------------------------------------------------------------------------------------
@@ -197,6 +236,15 @@ public:
 	virtual bool write(const device_queue& cqueue, const void* src, size_t src_size, uint3 offset, uint3 extent, uint2 mip_level_range,
 					   uint2 layer_range) {
 		if (!handle || !src) return false;
+		// write_check (device_image.cpp:503-547)
+		if (!has_flag<MEMORY_FLAG::HOST_WRITE>(flags)) {
+			FLB_LOG_ERROR("write: image is not host-writable");
+			return false;
+		}
+		if (src_size == 0) {
+			FLB_LOG_ERROR("write: trying to write 0 bytes!");
+			return false;
+		}
 		const uint32_t o[3] = { offset.x, offset.y, offset.z }, e[3] = { extent.x, extent.y, extent.z };
 		const uint32_t lv[2] = { mip_level_range.x, mip_level_range.y }, ly[2] = { layer_range.x, layer_range.y };
 		if (flmip_image_write(handle, src, src_size, o, e, lv, ly, const_cast<void*>(cqueue.get_queue_ptr())) != FLMIP_OK) {
@@ -375,6 +423,20 @@ public:
 protected:
 	uint32_t mappable_last_level() const { return generate_mip_maps ? 0u : mip_level_count - 1u; }
 
+	static std::mutex& minify_programs_mtx() {
+		static std::mutex m;
+		return m;
+	}
+	static std::unordered_map<const device_context*, std::shared_ptr<minify_program>>& minify_programs() {
+		static std::unordered_map<const device_context*, std::shared_ptr<minify_program>> progs;
+		return progs;
+	}
+	static std::shared_ptr<minify_program> lookup_minify_program(const device_context* ctx) {
+		std::lock_guard<std::mutex> lock(minify_programs_mtx());
+		const auto it = minify_programs().find(ctx);
+		return it != minify_programs().end() ? it->second : nullptr;
+	}
+
 	//! cuda_image::create_internal (cuda_image.cpp:158-539): allocate, initial copy unless NO_INITIAL_COPY, chain if GENERATE_MIP_MAPS
 	void create_internal(const device_queue& cqueue) {
 		const uint32_t dim[4] = { image_dim.x, image_dim.y, image_dim.z, image_dim.w };
@@ -468,6 +530,9 @@ public:
 			dev->type = device::TYPE(uint32_t(device::TYPE::GPU0) + uint32_t(devices.size()));
 			dev->name = info.name;
 			dev->units = info.units;
+			dev->clock = info.clock_mhz;
+			dev->mem_clock = info.mem_clock_mhz;
+			dev->mem_bus_width = info.mem_bus_width;
 			dev->global_mem_size = info.global_mem_size;
 			dev->max_total_local_size = info.max_total_local_size;
 			dev->max_image_2d_dim = { info.max_image_2d_dim[0], info.max_image_2d_dim[1] };
@@ -481,8 +546,16 @@ public:
 		}
 		for (const auto& dev : devices) default_queues.emplace_back(std::make_shared<device_queue>(*dev));
 		supported = !devices.empty();
+		// fastest device = highest cores per SM x units x clock; the first one wins ties (cuda_context.cpp:340-395; 128 cores per SM on sm_100)
+		for (const auto& dev : devices) {
+			const uint64_t score = 128ull * dev->units * dev->clock;
+			if (!fastest_gpu_device || score > fastest_gpu_score) {
+				fastest_gpu_device = dev.get();
+				fastest_gpu_score = score;
+			}
+		}
 	}
-	virtual ~device_context() = default;
+	virtual ~device_context() { device_image::provide_minify_program(*this, nullptr); }
 
 	bool is_supported() const { return supported; }
 	PLATFORM_TYPE get_platform_type() const { return PLATFORM_TYPE::CUDA; }
@@ -491,9 +564,11 @@ public:
 		for (const auto& d : devices) ret.push_back(d.get());
 		return ret;
 	}
-	//! device_context.hpp:106-116: GPU0 + n, FASTEST*, ANY; falls back to the first device like the reference
+	//! device_context::get_device (src/device/device_context.cpp:27-72): FASTEST / FASTEST_GPU -> the fastest GPU (there are no CPU
+	//! devices in a CUDA context), GPU0 + n -> that GPU, anything else / out of range -> "any" = the first device
 	const device* get_device(device::TYPE type) const {
 		if (devices.empty()) return nullptr;
+		if (type == device::TYPE::FASTEST || type == device::TYPE::FASTEST_GPU) return fastest_gpu_device;
 		const uint32_t t = uint32_t(type);
 		if (t >= uint32_t(device::TYPE::GPU0) && t <= uint32_t(device::TYPE::GPU255)) {
 			const uint32_t idx = t - uint32_t(device::TYPE::GPU0);
@@ -544,6 +619,8 @@ protected:
 	std::vector<std::unique_ptr<cuda_device>> devices;
 	std::vector<std::shared_ptr<device_queue>> default_queues;
 	bool supported { false };
+	const device* fastest_gpu_device { nullptr };
+	uint64_t fastest_gpu_score { 0 };
 };
 using cuda_context = device_context;
 

@@ -49,6 +49,10 @@ typedef struct flmip_device_info {
 	uint32_t max_image_2d_dim[2], max_image_3d_dim[3];
 	uint32_t max_mip_levels;
 	uint32_t driver_version;
+	uint32_t clock_mhz;             /* SM clock                     (fl::device::clock; FASTEST_GPU score = units x clock, cuda_context.cpp:340-395) */
+	uint32_t mem_clock_mhz;         /* fl::device::mem_clock */
+	uint32_t mem_bus_width;         /* fl::device::mem_bus_width */
+	uint32_t l2_cache_size;         /* bytes */
 } flmip_device_info;
 
 typedef struct flmip_level_info {
@@ -77,8 +81,11 @@ int flmip_event_record(int device, flmip_event ev, flmip_stream stream);
 int flmip_event_sync(int device, flmip_event ev);
 int flmip_event_elapsed_ms(int device, flmip_event start, flmip_event stop, float* ms);
 int flmip_event_destroy(int device, flmip_event ev);
-/* page-locked host staging buffers */
+/* page-locked host staging buffers; FLMIP_HOST_WRITE_COMBINED: upload-only buffers (fast for the GPU to read over PCIe, slow for
+ * the CPU to read) */
+#define FLMIP_HOST_WRITE_COMBINED 1u
 int flmip_host_alloc(int device, size_t size, void** out);
+int flmip_host_alloc_ex(int device, size_t size, uint32_t flags, void** out);
 int flmip_host_free(int device, void* ptr);
 
 /* -- images: cuda_image::create_internal (src/device/cuda/cuda_image.cpp:158-539), but as ONE linear
@@ -87,6 +94,17 @@ int flmip_host_free(int device, void* ptr);
  *    image_dim = (w, h, d or layers, layers-for-3D); cube: 6 faces per layer (image_types.hpp:716-726). */
 int flmip_image_create(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags,
 					   flmip_image* out);
+/* Opt-in for other contexts (the counterpart of device_image::provide_minify_program, src/device/device_image.cpp:155-194, which
+ * registers a minify program per device_context): a context that already owns its CUcontext and its image memory hands both in
+ * instead of adopting this library's allocations.
+ *   flmip_device_attach_context: run `device` on the caller's CUcontext (floor's cuda_context creates its own with cuCtxCreate,
+ *     cuda_context.cpp:117-124) instead of the primary one; must precede the first use of the device.
+ *   flmip_image_create_external: an image over caller-owned LINEAR device memory in floor's host layout (level-major, tight rows,
+ *     `size` >= image_data_size over all levels, 16-byte aligned); destroy releases the handle and its counters, never the memory.
+ * Opaque tiled images (CUmipmappedArray) go through flmip_image_copy_{from,to}_tiled below. */
+int flmip_device_attach_context(int device, void* cu_context);
+int flmip_image_create_external(int device, uint64_t image_type, const uint32_t image_dim[4], uint32_t mip_level_limit, uint32_t flags,
+								uint64_t device_ptr, uint64_t size, flmip_image* out);
 int flmip_image_destroy(flmip_image img);
 int flmip_image_mip_level_count(flmip_image img, uint32_t* out);
 int flmip_image_layer_count(flmip_image img, uint32_t* out);
@@ -100,8 +118,14 @@ int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast
  *    Whole levels [level_first, level_last] (inclusive, like mip_level_range) in host layout; async on `stream`. */
 int flmip_image_upload(flmip_image img, const void* src, size_t src_size, uint32_t level_first, uint32_t level_last, flmip_stream stream);
 int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, flmip_stream stream);
+/* layers [layer_first, layer_first + layer_count) of levels [level_first, level_last], level-major like an image of layer_count
+ * layers (validation of sampled layers of images too large to read back whole; the reference's map() has no ranges) */
+int flmip_image_download_layers(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, uint32_t layer_first,
+								uint32_t layer_count, flmip_stream stream);
 /* sub-region write with floor's semantics (offset / extent in level-0 texels, inclusive level and layer ranges,
- * source tightly packed per level): cuda_image::write, cuda_image.cpp:588-673 */
+ * source tightly packed per level): cuda_image::write, cuda_image.cpp:588-673.  Every level of the range is validated before the
+ * first copy: a region that leaves a level (odd dims: offset >> level + max(extent >> level, 1) > dim >> level) fails with
+ * FLMIP_ERR_INVALID and writes nothing -- the reference's cuMemcpy3D into the level's CUarray fails at that level. */
 int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
 					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream);
 int flmip_image_zero(flmip_image img, flmip_stream stream);          /* cuda_image::zero, cuda_image.cpp:675-701 */
@@ -125,7 +149,12 @@ int flmip_device_cu_context(int device, void** out);
 /* -- THE hot path: device_image::generate_mip_map_chain (src/device/device_image.cpp:235-328) + the
  *    libfloor_mip_map_minify_* kernels (include/floor/device/backend/mip_map_minify.hpp:89-126).
  *    Enqueues on `stream` and returns; the C++ drop-in adds the blocking flmip_stream_sync the reference
- *    implies (wait_until_completion = true, device_image.cpp:322). */
+ *    implies (wait_until_completion = true, device_image.cpp:322).
+ *    ONE chain per image is in flight at a time (the launch shares the image's tile / group / layer counters): chains enqueued on
+ *    one stream are ordered by the stream; a chain enqueued on a different stream than the image's previous one first makes that
+ *    stream wait for everything enqueued on the old stream so far (event hand-over inside this call; also across
+ *    flmip_stream_destroy and flmip_batch_generate).  Callable from any thread; calls on one image serialise on a per-image lock.
+ *    first_level >= mip level count fails with FLMIP_ERR_INVALID; first_level == last level generates nothing. */
 int flmip_mip_chain_generate(flmip_image img, flmip_stream stream);
 /* regenerate only levels > first_level (dirty-level update); first_level = 0 is the full chain */
 int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_stream stream);

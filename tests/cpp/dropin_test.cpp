@@ -183,6 +183,51 @@ int main(int argc, char** argv) {
 			CHECK(got == wants[i]);
 		}
 	}
+	// provide_minify_program (device_image.cpp:155-194): a context-registered program receives the chains of that context's images
+	{
+		++current_case;
+		struct counting_program : minify_program {
+			int calls = 0;
+			uint32_t last_first_level = ~0u;
+			bool minify(device_image& img, const device_queue& cqueue, uint32_t first_level) override {
+				++calls;
+				last_first_level = first_level;
+				return device_image::builtin_minify_program()->minify(img, cqueue, first_level);
+			}
+		};
+		auto prog = std::make_shared<counting_program>();
+		CHECK(device_image::provide_minify_program(ctx, prog));
+		const uint4 dim { 512, 256, 0, 0 };
+		const uint32_t d[4] = { dim.x, dim.y, 0, 0 };
+		const IMAGE_TYPE type = IMAGE_TYPE::IMAGE_2D | IMAGE_TYPE::RGBA8 | IMAGE_TYPE::FLAG_MIPMAPPED | IMAGE_TYPE::READ_WRITE;
+		const size_t l0_size = image_data_size_from_types(dim, type, true), all_size = image_data_size_from_types(dim, type);
+		std::vector<uint8_t> want(all_size), got(all_size), l0(l0_size);
+		flo_fill(l0.data(), d, image_type_bits(type), 12, 0, 1);
+		std::memcpy(want.data(), l0.data(), l0_size);
+		CHECK(flo_generate(want.data(), d, image_type_bits(type), 0, 0, 8) == 0);
+		auto img = ctx.create_image(*queue, dim, type, l0, MEMORY_FLAG::READ_WRITE | MEMORY_FLAG::HOST_READ_WRITE | MEMORY_FLAG::GENERATE_MIP_MAPS);
+		CHECK(img != nullptr && prog->calls == 1 && prog->last_first_level == 0u);
+		if (img) {
+			CHECK(img->read_levels(*queue, got.data(), got.size(), 0, img->get_mip_level_count() - 1));
+			CHECK(got == want);
+			CHECK(img->generate_mip_map_chain_async(*queue, 3u) && prog->calls == 2 && prog->last_first_level == 3u);
+			queue->finish();
+		}
+		// another context is not affected; nullptr restores the built-in program
+		CHECK(device_image::provide_minify_program(ctx, nullptr));
+		if (img) {
+			img->generate_mip_map_chain(*queue);
+			CHECK(prog->calls == 2);
+		}
+		// a host-read-only image refuses write() (write_check, device_image.cpp:503-547), and so does a zero-size source
+		auto ro = ctx.create_image(*queue, dim, type, MEMORY_FLAG::READ_WRITE | MEMORY_FLAG::HOST_READ);
+		CHECK(ro != nullptr && !ro->write(*queue, l0.data(), l0.size(), { 0, 0, 0 }, { dim.x, dim.y, 1 }, { 0, 0 }, { 0, 0 }));
+		CHECK(img && !img->write(*queue, l0.data(), 0, { 0, 0, 0 }, { dim.x, dim.y, 1 }, { 0, 0 }, { 0, 0 }));
+		// FASTEST_GPU: highest units x clock (cuda_context.cpp:340-395)
+		const device* fastest = ctx.get_device(device::TYPE::FASTEST_GPU);
+		CHECK(fastest != nullptr && fastest->clock > 0u);
+		for (const device* d2 : ctx.get_devices()) CHECK(uint64_t(d2->units) * d2->clock <= uint64_t(fastest->units) * fastest->clock);
+	}
 	// constructor invariants throw (device_image.hpp:502-539); unsupported formats return nullptr (cuda_image.cpp:173-180)
 	bool threw = false;
 	try {
