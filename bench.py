@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- mip-chain throughput of the B200-native path (and of the CPU reference arm).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl ours|reference|incumbent]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full mip chain (device_image::generate_mip_map_chain) over one batch of synthetic input.
@@ -404,6 +404,21 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu(args.workload, steps=None, warmup=0)
 
+    # the reference's own GPU kernels on the same box (GPU over GPU): the headline workload, plus a C3 shard and C5 for the default line
+    gpu_incumbent = None
+    if rank == 0 and world == 1 and not args.no_incumbent:
+        gpu_incumbent = {}
+        for wl in ([args.workload] + (["c3", "c5"] if args.workload == "c2" else [])):
+            inc = run_incumbent(wl, steps=max(3, min(args.steps, 10)), warmup=2, device=local_rank)
+            if "value" in inc:
+                ours = R["achieved"] if wl == args.workload else None
+                if ours is None and layered and wl in layered and "per_gpu_achieved" in layered[wl]:
+                    ours = layered[wl]["per_gpu_achieved"]
+                if ours is not None:
+                    inc["speedup_vs_blocking"] = round(ours / inc["value"], 2)
+                    inc["speedup_vs_enqueued"] = round(ours / inc["enqueued_value"], 2)
+            gpu_incumbent[wl] = inc
+
     if rank == 0:
         plan = R["plan"]
         e2e = None
@@ -433,6 +448,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": R["launches"],
             "clocks": R["clocks"],
             "cpu_baseline": cpu_baseline,
+            "gpu_incumbent": gpu_incumbent,
             "device": dev.name,
         }
         print(json.dumps(out), flush=True)
@@ -487,6 +503,53 @@ def run_cpu(workload: str, steps: int, warmup: int):
             "seconds_per_step": round(dt, 4), "bytes_per_step": int(total)}
 
 
+def run_incumbent(workload: str, steps: int, warmup: int, device: int = 0):
+    """The reference's OWN GPU path on this box (bench infrastructure, oracle/incumbent_harness.cpp): its prebuilt sm_50 PTX kernels
+    (tex.level + sust, extracted from mmm.fubar into oracle/_ref) JIT-compiled for the B200, on a CUmipmappedArray, behind its own
+    loop of one BLOCKING launch per (layer, level) (device_image.cpp:304-327).  `value` = that loop as an application pays it;
+    `enqueued_value` = the same launches without the per-launch sync between CUDA events (the kernels alone)."""
+    import oracle
+    from oracle import incumbent
+    desc, dim, t, sharded, cid = WORKLOADS[workload]
+    if not incumbent.available():
+        return {"unavailable": "oracle/_ref/mmm_incumbent.ptx or libfloor_incumbent.so missing (python oracle/build_incumbent.py needs /root/reference)"}
+    if t & T.FLAG_CUBE:
+        return {"unavailable": "the reference has no minify kernel for cube images (mip_map_minify.hpp:95-97; lookup fails device_image.cpp:278-283)"}
+    sdim = list(dim)
+    sample = "full workload image"
+    if sharded or workload == "n2":
+        sdim[2] = min(dim[2], 64)
+        sample = f"{sdim[2]} of {dim[2]} layers (the reference loops layers outermost: cost is linear in the layer count)"
+    sdim = tuple(sdim)
+    l0 = oracle.fill_synthetic(sdim, t, cid)
+    total = oracle.image_data_size(sdim, t)
+    out = np.zeros(total, dtype=np.uint8)
+    try:
+        blocking_ms, enq_ms, launches = incumbent.run(sdim, t, l0, warmup, steps, device, out)
+    except RuntimeError as e:
+        return {"unavailable": str(e)[:300]}
+    want = oracle.generate_mip_map_chain(l0, sdim, t, threads=min(os.cpu_count() or 8, 32))
+    n0 = l0.size
+    differing = float(np.count_nonzero(out[n0:] != want[n0:])) / max(total - n0, 1)
+    return {"value": round(total / blocking_ms / 1e6, 2), "unit": "GB/s", "ms_per_step": round(blocking_ms, 4), "launches": int(launches),
+            "enqueued_value": round(total / enq_ms / 1e6, 2), "enqueued_ms_per_step": round(enq_ms, 4), "bytes_per_step": int(total), "sample": sample,
+            "steps": steps, "kind": "reference's prebuilt sm_50 PTX (mmm.fubar binary #7), JIT for this GPU with MAX_REGISTERS=32 / O4, CUmipmappedArray + tex.level.* + sust.b.*, "
+                                    "one blocking launch per (layer, level)",
+            "bytes_differing_from_host_compute": round(differing, 6),
+            "note": "not the parity target: the texture unit filters with 9-bit fixed-point weights (SURVEY 8a row 14)"}
+
+
+def run_incumbent_arm(args, rank, world):
+    if rank != 0:
+        return
+    inc = run_incumbent(args.workload, args.steps, args.warmup, int(os.environ.get("LOCAL_RANK", "0")))
+    out = {"impl": "incumbent", "metric": "mip_chain_throughput", "value": inc.get("value"), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": inc.get("ms_per_step"), "higher_is_better": True, "scaling": "strong" if WORKLOADS[args.workload][3] else "weak",
+           "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
+           "config": config_for(args.workload, world, args.layers), "gpu_incumbent": inc}
+    print(json.dumps(out), flush=True)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -509,7 +572,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "incumbent"])
+    ap.add_argument("--no-incumbent", action="store_true", help="tuning runs only: skip the reference's own GPU kernels (gpu_incumbent)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="tuning runs only: override the layer / cube count of c3 / c4")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
@@ -522,6 +586,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.impl == "incumbent":
+        run_incumbent_arm(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
 
