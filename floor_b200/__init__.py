@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 FLMIP_OK = 0
 ERR_NO_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_DRIVER, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
-IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED = 1, 2, 4, 8, 16
+IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED, IMAGE_NO_TMA_TILES = 1, 2, 4, 8, 16, 32
 HOST_WRITE_COMBINED = 1
 
 # every symbol include/floor_b200_mip.h declares (checked by tests/test_cabi.py without a GPU)
@@ -30,7 +30,7 @@ EXPORTS = [
     "flmip_host_alloc", "flmip_host_alloc_ex", "flmip_host_free",
     "flmip_device_attach_context", "flmip_image_create_external", "flmip_image_download_layers",
     "flmip_image_create", "flmip_image_destroy", "flmip_image_mip_level_count", "flmip_image_layer_count",
-    "flmip_image_data_size", "flmip_image_get_level_info", "flmip_image_device_ptr", "flmip_image_plan",
+    "flmip_image_data_size", "flmip_image_get_level_info", "flmip_image_device_ptr", "flmip_image_plan", "flmip_image_plan_tma_tile_launches", "flmip_sampler_table_entry",
     "flmip_image_upload", "flmip_image_download", "flmip_image_write", "flmip_image_zero",
     "flmip_mip_chain_generate", "flmip_mip_chain_generate_from", "flmip_image_fill_synthetic",
     "flmip_image_blit", "flmip_image_create_tiled_twin", "flmip_tiled_destroy", "flmip_image_copy_to_tiled",
@@ -113,6 +113,8 @@ def lib() -> ctypes.CDLL:
         "flmip_image_get_level_info": (i32, [vp, u32, ctypes.POINTER(LevelInfo)]),
         "flmip_image_device_ptr": (i32, [vp, ctypes.POINTER(u64)]),
         "flmip_image_plan": (i32, [vp, u32p, u32p, u32p]),
+        "flmip_image_plan_tma_tile_launches": (i32, [vp, u32p]),
+        "flmip_sampler_table_entry": (i32, [u32, u32, u32p]),
         "flmip_image_upload": (i32, [vp, vp, ctypes.c_size_t, u32, u32, vp]),
         "flmip_image_download": (i32, [vp, vp, ctypes.c_size_t, u32, u32, vp]),
         "flmip_image_write": (i32, [vp, vp, ctypes.c_size_t, u32p, u32p, u32p, u32p, vp]),

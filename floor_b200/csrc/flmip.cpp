@@ -54,7 +54,7 @@ int fail(int code, const char* fmt, ...) {
 	F(cuEventCreate) F(cuEventRecord) F(cuEventSynchronize) F(cuEventElapsedTime) F(cuEventDestroy) F(cuModuleLoadData)          \
 	F(cuModuleGetFunction) F(cuFuncSetAttribute) F(cuLaunchKernel) F(cuLaunchKernelEx) F(cuTensorMapEncodeTiled) F(cuMemcpyDtoDAsync)                 \
 	F(cuMipmappedArrayCreate) F(cuMipmappedArrayGetLevel) F(cuMipmappedArrayDestroy) F(cuGraphCreate) F(cuGraphAddKernelNode)           \
-	F(cuGraphInstantiate) F(cuGraphLaunch) F(cuGraphExecDestroy) F(cuGraphDestroy) F(cuStreamWaitEvent) F(cuCtxGetDevice)
+	F(cuGraphInstantiate) F(cuGraphLaunch) F(cuGraphExecDestroy) F(cuGraphDestroy) F(cuStreamWaitEvent) F(cuCtxGetDevice) F(cuMemcpyHtoD)
 
 struct driver_api {
 #define FL_DECL(name) decltype(&name) p_##name = nullptr;
@@ -315,7 +315,7 @@ struct flmip_image_s {
 	int device = 0;
 	uint64_t type = 0;
 	uint32_t dim[4] = { 0, 0, 0, 0 };
-	uint32_t dc = 0, channels = 0, bpc = 0, bpp = 0, layers = 0, level_count = 0, elem_kind = 0, no_double = 0;
+	uint32_t dc = 0, channels = 0, bpc = 0, bpp = 0, layers = 0, level_count = 0, elem_kind = 0, no_double = 0, sm_count = 0;
 	flmip_level_info levels[FLMIP_MAX_LEVELS] {};
 	uint64_t total_size = 0;
 	CUdeviceptr mem = 0, counters = 0;
@@ -330,6 +330,16 @@ struct flmip_image_s {
 	// levels the single-pass launch does not produce: multi-level tile kernel (2D / 3D) or one generic launch per level
 	bool tiled = false;
 	std::string tile_name;
+	// persistent TMA tile kernel (flmip_ptile2d_*): sampler table, per-layer counters + scheduler words, one tensor map per source level
+	bool ptile = false;
+	uint32_t ptile_flags = 0; // FLMIP_IMAGE_TMA_TILES_* tuning overrides
+	std::string ptile_name;
+	CUdeviceptr wtab = 0, pcounters = 0;
+	uint32_t wtab_off[FLMIP_MAX_LEVELS][2] = {};
+	bool texel2[FLMIP_MAX_LEVELS][2] = {}; // destination level / axis whose texel 0 takes the reference's texel-2 fetch
+	uint32_t ptile_smem = 0;
+	CUtensorMap ptile_map[FLMIP_MAX_LEVELS];
+	bool ptile_map_valid[FLMIP_MAX_LEVELS] = {};
 	bool external_mem = false; // `mem` belongs to the caller (flmip_image_create_external): never freed here
 	// One chain per image may be in flight at a time: the group / layer / scheduler counters beside the image are shared by every
 	// launch on it.  Chains on ONE stream are ordered by the stream; when a chain is enqueued on a different stream than the
@@ -613,12 +623,14 @@ uint32_t tile_levels_from(const flmip_image_s& im, uint32_t s, uint32_t pop) {
 }
 
 // number of tile-kernel launches that produce levels (src_level, populated)
-uint32_t tile_launch_count(const flmip_image_s& im, uint32_t src_level) {
-	const uint32_t pop = populated_levels(im);
-	uint32_t n = 0;
-	for (uint32_t s = src_level; s + 1 < pop; s += tile_levels_from(im, s, pop)) ++n;
-	return n;
-}
+// what one launch of the persistent tile kernel produces from source level `src`
+struct ptile_step {
+	bool ok = false;
+	uint32_t tile_last = 0, last = 0;
+};
+ptile_step plan_ptile_step(const flmip_image_s& im, uint32_t src, uint32_t pop);
+int launch_ptile(flmip_image_s& im, device_state* ds, uint32_t src, const ptile_step& st, CUstream stream);
+uint32_t tile_launch_count(const flmip_image_s& im, uint32_t src_level, uint32_t* tma_launches);
 
 // multi-level tile kernel: levels src_level + 1 ... (stream-ordered launches of up to 6 (2D) / 4 (3D) levels each)
 int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, CUstream stream) {
@@ -626,6 +638,15 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 	CUfunction fn = nullptr;
 	uint32_t step = 0;
 	for (uint32_t s = src_level; s + 1 < pop; s += step) {
+		// the persistent TMA kernel where the level qualifies as a source (it may finish the whole chain) ...
+		const ptile_step pst = plan_ptile_step(im, s, pop);
+		if (pst.ok) {
+			const int rc = launch_ptile(im, ds, s, pst, stream);
+			if (rc != FLMIP_OK) return rc;
+			step = pst.last - s;
+			continue;
+		}
+		// ... else the LDG tile kernel: any size, up to 6 (2D) / 4 (3D) levels per launch
 		step = tile_levels_from(im, s, pop);
 		if (!fn) {
 			const int rc = get_function(ds, im.tile_name, 0, &fn);
@@ -663,6 +684,186 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 		if (rc != FLMIP_OK) return rc;
 	}
 	return FLMIP_OK;
+}
+
+// ---- persistent TMA tile kernel: sampler table and launch plan --------------------------------------------------------
+// One table entry: the reference's linear fetch for destination texel g along one axis of a source level of n texels
+// (mip_map_minify.hpp:106, host_image.hpp:141-174, 869-894), evaluated with the same IEEE fp32 operations as axis_fetch() /
+// generic_texel() in mip_kernels.cu (this file is built with -fno-fast-math -ffp-contract=off).  Returns false if the fetch is
+// none of the three shapes the table can express (never observed: tests/test_npot_weights.py).
+bool sampler_entry(uint32_t g, uint32_t n, uint32_t* out) {
+	const volatile float fdim = (float)n;
+	const volatile float inv_prev = 1.0f / fdim;                     // device_image.cpp:311-312
+	const volatile float fdim_excl = nextafterf(fdim, 0.0f);           // host_image.cpp:102-107
+	const volatile float coord = (float)(g * 2u + 1u) * inv_prev;
+	if (!(coord >= 0.0f && coord < 1.0f)) return false;              // wrap(coord, 1) would not be the identity
+	const volatile float m = coord * fdim;
+	const volatile float frac = m - floorf(m);
+	const bool lo = frac < 0.5f;
+	volatile float t = lo ? frac + 0.5f : 1.5f - frac;
+	volatile float ma = m + (lo ? -1.0f : 1.0f);
+	const float mb = m > fdim_excl ? fdim_excl : m;
+	const float mac = ma > fdim_excl ? fdim_excl : (ma < 0.0f ? 0.0f : ma);
+	const uint32_t b = (uint32_t)(long long)mb, a = (uint32_t)(long long)mac;
+	uint32_t bits;
+	const float tv = t;
+	memcpy(&bits, &tv, 4);
+	if (bits == 0u || (bits & 0xC0000000u)) return false;           // 0 < t < 2 keeps the two flag bits free
+	if (a == 2u * g && b == 2u * g + 1u) *out = bits;
+	else if (a == 2u * g + 1u && b == 2u * g) *out = bits | FLMIP_WTAB_SWAP;
+	else if (g == 0u && a == 2u && b == 0u) *out = bits | FLMIP_WTAB_TEXEL2;
+	else return false;
+	return true;
+}
+
+constexpr uint32_t WTAB_PAD = 512u; // consumers of a border tile read entries past the level's extent (results masked)
+
+int build_sampler_table(flmip_image_s& im, device_state* ds) {
+	(void)ds;
+	std::vector<uint32_t> tab;
+	const uint32_t pop = populated_levels(im);
+	for (uint32_t L = 1; L < pop; ++L) {
+		for (uint32_t d = 0; d < 2; ++d) {
+			while (tab.size() % 4u) tab.push_back(0x3F000000u); // segments start on 16-byte boundaries
+			im.wtab_off[L][d] = (uint32_t)tab.size();
+			const uint32_t n_dst = im.levels[L].dim[d], n_src = im.levels[L - 1].dim[d];
+			for (uint32_t g = 0; g < n_dst; ++g) {
+				uint32_t e = 0;
+				if (!sampler_entry(g, n_src, &e)) return fail(FLMIP_ERR_UNSUPPORTED, "irregular sampler fetch at level %u axis %u texel %u", L, d, g);
+				if (e & FLMIP_WTAB_TEXEL2) im.texel2[L][d] = true;
+				tab.push_back(e);
+			}
+			for (uint32_t i = 0; i < WTAB_PAD; ++i) tab.push_back(0x3F000000u);
+		}
+	}
+	if (tab.empty()) return fail(FLMIP_ERR_INVALID, "no levels to generate");
+	CU_TRY(cu.p_cuMemAlloc(&im.wtab, tab.size() * sizeof(uint32_t)), "cuMemAlloc(sampler table)");
+	CU_TRY(cu.p_cuMemcpyHtoD(im.wtab, tab.data(), tab.size() * sizeof(uint32_t)), "cuMemcpyHtoD(sampler table)");
+	return FLMIP_OK;
+}
+
+ptile_step plan_ptile_step(const flmip_image_s& im, uint32_t src, uint32_t pop) {
+	ptile_step st;
+	if (!im.ptile || src + 1u >= pop) return st;
+	const flmip_level_info& ls = im.levels[src];
+	const uint64_t pitch = (uint64_t)ls.dim[0] * im.bpp;
+	// TMA: 16-byte aligned base and row pitch; a whole tile row / column must exist (smaller images are latency-bound anyway)
+	if (((im.mem + ls.offset) & 15u) || (pitch & 15u) || pitch < im.tiling.tile_bytes_x || ls.dim[1] < im.tiling.ty) return st;
+	if (pitch >= (1ull << 32) * 4ull) return st;
+	// levels src + 1 and src + 2 are produced in registers from texels {2g, 2g + 1}: no texel-2 fetch there
+	for (uint32_t k = src + 1u; k <= src + 2u && k < pop; ++k)
+		if (im.texel2[k][0] || im.texel2[k][1]) return st;
+	const uint64_t tiles = (uint64_t)((ls.dim[0] + im.tiling.tx - 1u) / im.tiling.tx) * ((ls.dim[1] + im.tiling.ty - 1u) / im.tiling.ty) * im.layers;
+	if (tiles > 0x7FFFFFFFull) return st;
+	// When does the persistent kernel pay off?  Measured against the LDG tile kernel over sizes and formats (scripts/ptile_sweep.py,
+	// profiles/r2/05_ptile_plan_sweep.txt), per resident CTA (2 per SM):
+	//  * its launch has a fixed cost of ~15 us (ring ramp-up, 3.4 tiles per CTA already take 13 us: scripts/timeline_ptile.py) against
+	//    ~5 us of the LDG kernel, so a level with few tiles per CTA is better off there (3840 x 2160 RGBA8: 21 us against 31 .. 38 us);
+	//  * streaming, it beats the LDG kernel the more the narrower the texels are: R8 2 216 against 1 008 GB/s, RGBA8 3 765 against
+	//    2 794 GB/s, RGBA16F 6 950 against 5 650 GB/s (levels 1 - 2 of 64 x 1920 x 1080), while 16-byte texels already run at the copy
+	//    peak with plain loads (7 078 GB/s) -- never taken for those.
+	const uint64_t resident_ctas = 2ull * im.sm_count;
+	static const uint32_t env_min = env_u32("FLMIP_PTILE_MIN_TILES_PER_CTA", 0);
+	const uint32_t min_tiles = env_min ? env_min : (im.bpp == 1 ? 3u : im.bpp == 2 ? 6u : im.bpp == 4 ? 12u : im.bpp == 8 ? 48u : 0xFFFFFFFFu);
+	if (!(im.ptile_flags & FLMIP_IMAGE_TMA_TILES_ALWAYS) && (min_tiles == 0xFFFFFFFFu || tiles < (uint64_t)min_tiles * resident_ctas)) return st;
+	uint32_t tile_last = src + im.tiling.tile_levels < pop - 1u ? src + im.tiling.tile_levels : pop - 1u;
+	// a texel-2 fetch needs 3 texels of the previous level inside the tile's part of it
+	for (uint32_t k = src + 3u; k <= tile_last; ++k) {
+		const uint32_t w = im.tiling.tx >> (k - 1u - src), h = im.tiling.ty >> (k - 1u - src);
+		if ((w < 3u && im.texel2[k][0]) || (h < 3u && im.texel2[k][1])) { tile_last = k - 1u; break; }
+	}
+	st.ok = true;
+	// By default a launch streams levels src + 1 and src + 2 only: the consumers produce both in registers, the finisher pool stays
+	// idle and the kernel runs at the roofline (N2: 0.204 ms for 98.4 % of the bytes; with the pool reducing every tile further and
+	// the last tile of a layer finishing the chain it is 0.27 ms, finisher-bound).  The rest of the chain, 1 / 16 of the texels, goes
+	// through this planner again from level src + 2 (usually: the LDG kernel).  FLMIP_IMAGE_TMA_TILES_NO_SPLIT selects the
+	// one-launch form (validation, tuning).
+	const bool split = !(im.ptile_flags & FLMIP_IMAGE_TMA_TILES_NO_SPLIT);
+	if (split && src + 2u < pop - 1u) {
+		st.tile_last = st.last = src + 2u;
+		return st;
+	}
+	st.tile_last = tile_last;
+	st.last = tile_last;
+	if (tile_last < pop - 1u) {
+		const flmip_level_info& lt = im.levels[tile_last];
+		if (lt.slice_size <= FLMIP_PTILE_PATCH_BYTES) st.last = pop - 1u; // the last tile of a layer finishes the chain in the same launch
+	}
+	return st;
+}
+
+int launch_ptile(flmip_image_s& im, device_state* ds, uint32_t src, const ptile_step& st, CUstream stream) {
+	const flmip_level_info& ls = im.levels[src];
+	if (!im.ptile_map_valid[src]) {
+		const cuuint64_t row_bytes = (cuuint64_t)ls.dim[0] * im.bpp;
+		cuuint64_t gdim[3] = { row_bytes / 4u, ls.dim[1], im.layers };
+		cuuint64_t gstride[2] = { row_bytes, row_bytes * ls.dim[1] };
+		cuuint32_t box[3] = { im.tiling.tile_bytes_x / 4u, im.tiling.ty, 1u };
+		cuuint32_t estride[3] = { 1, 1, 1 };
+		// what lies outside the level is filled with zeros (partial tiles at the right / bottom border)
+		CU_TRY(cu.p_cuTensorMapEncodeTiled(&im.ptile_map[src], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, reinterpret_cast<void*>(im.mem + ls.offset), gdim, gstride, box,
+										   estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+										   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+			   "cuTensorMapEncodeTiled(tile kernel)");
+		im.ptile_map_valid[src] = true;
+	}
+	flmip_ptile_params P;
+	memset(&P, 0, sizeof(P));
+	P.base = im.mem;
+	for (uint32_t l = 0; l < im.level_count; ++l) {
+		P.level_off[l] = im.levels[l].offset;
+		P.dim[l][0] = im.levels[l].dim[0];
+		P.dim[l][1] = im.levels[l].dim[1];
+		P.wtab_off[l][0] = im.wtab_off[l][0];
+		P.wtab_off[l][1] = im.wtab_off[l][1];
+	}
+	P.wtab = im.wtab;
+	P.counters = im.pcounters;
+	P.sched = im.pcounters + (uint64_t)im.layers * sizeof(uint32_t);
+	P.src_level = src;
+	P.tile_last = st.tile_last;
+	P.last_level = st.last;
+	P.tiles[0] = (ls.dim[0] + im.tiling.tx - 1u) / im.tiling.tx;
+	P.tiles[1] = (ls.dim[1] + im.tiling.ty - 1u) / im.tiling.ty;
+	P.layers = im.layers;
+	P.total_tiles = P.tiles[0] * P.tiles[1] * im.layers;
+	P.stages = 2;
+	P.no_double = im.no_double;
+	// units of 4 tiles (one publish per unit) once every resident CTA has many tiles to work through; below that the pool keeps up
+	// with one publish per tile, and units would only coarsen what the scheduler can balance
+	const uint64_t resident_ctas = 2ull * ds->info.units;
+	static const uint32_t env_unit_tiles = env_u32("FLMIP_PTILE_UNIT_MIN_TILES_PER_CTA", 8);
+	P.unit_shift = (st.last > st.tile_last && P.total_tiles >= env_unit_tiles * resident_ctas) ? 2u : 0u;
+	// full-width vector stores need every row of the level to start on a 16- / 8-byte boundary
+	const flmip_level_info& l1 = im.levels[src + 1u];
+	const uint64_t pitch1 = (uint64_t)l1.dim[0] * im.bpp;
+	P.vec1 = (((im.mem + l1.offset) | l1.slice_size | pitch1) & 15u) == 0u;
+	if (src + 2u < im.level_count) {
+		const flmip_level_info& l2 = im.levels[src + 2u];
+		const uint64_t pitch2 = (uint64_t)l2.dim[0] * im.bpp, mask = im.bpp == 16 ? 15u : 7u;
+		P.vec2 = (((im.mem + l2.offset) | l2.slice_size | pitch2) & mask) == 0u;
+	}
+	CUfunction fn = nullptr;
+	const int rc = get_function(ds, im.ptile_name, im.ptile_smem, &fn);
+	if (rc != FLMIP_OK) return rc;
+	const uint64_t units = ((uint64_t)P.total_tiles + (1u << P.unit_shift) - 1u) >> P.unit_shift;
+	const uint64_t grid = units < resident_ctas ? units : resident_ctas;
+	void* args[] = { &im.ptile_map[src], &P };
+	return launch(fn, grid, FLMIP_BLOCK_THREADS, im.ptile_smem, stream, args, true);
+}
+
+// number of launches that produce levels (src_level, populated): persistent TMA tile kernel where a level qualifies as its source
+uint32_t tile_launch_count(const flmip_image_s& im, uint32_t src_level, uint32_t* tma_launches) {
+	const uint32_t pop = populated_levels(im);
+	uint32_t n = 0, tma = 0;
+	for (uint32_t s = src_level; s + 1 < pop;) {
+		const ptile_step pst = plan_ptile_step(im, s, pop);
+		if (pst.ok) { s = pst.last; ++tma; }
+		else s += tile_levels_from(im, s, pop);
+		++n;
+	}
+	if (tma_launches) *tma_launches = tma;
+	return n;
 }
 
 int check_image(flmip_image img) {
@@ -861,8 +1062,58 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 			rc = get_function(ds, im->tile_name, 0, &fn); // resolve now: fail at creation, not at first use
 		}
 	}
+	// persistent TMA tile kernel for what the single-pass kernel does not take (2D, incl. arrays / cubes): optional, like the
+	// single-pass plan -- when any of its steps fails the LDG tile kernel serves the image
+	static const bool env_no_tma_tiles = env_u32("FLMIP_NO_TMA_TILES", 0) != 0; // A/B tuning runs
+	if (rc == FLMIP_OK && im->tiled && im->dc == 2 && !(flags & FLMIP_IMAGE_NO_TMA_TILES) && !env_no_tma_tiles && populated_levels(*im) > 1u &&
+		(!im->fast || im->fast_level_count < populated_levels(*im))) {
+		im->tiling = flmip_tiling_lookup(im->bpp, 2);
+		im->sm_count = ds->info.units;
+		im->ptile_flags = flags;
+		char name[64];
+		snprintf(name, sizeof(name), "flmip_ptile2d_k%u_c%u", im->elem_kind, im->channels);
+		im->ptile_name = name;
+		im->ptile_smem = 2u * im->tiling.tile_bytes + FLMIP_FINISHER_WARPS * (im->tiling.cascade_bytes + im->tiling.cascade_bytes / 4u) +
+						 FLMIP_PTILE_PATCH_BYTES + FLMIP_PTILE_PATCH_BYTES / 4u;
+		CUfunction fn = nullptr;
+		int prc = get_function(ds, im->ptile_name, im->ptile_smem, &fn);
+		if (prc == FLMIP_OK) prc = build_sampler_table(*im, ds);
+		if (prc == FLMIP_OK) {
+#ifdef FLMIP_TIMELINE
+			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 4u * 1024u; // + 4 x u64 per CTA behind the scheduler words (tuning builds)
+#else
+			const size_t n_pc = (size_t)im->layers + 2u;
+#endif
+			const CUresult r = cu.p_cuMemAlloc(&im->pcounters, n_pc * sizeof(uint32_t));
+			if (r != CUDA_SUCCESS) prc = cu_fail(r, "cuMemAlloc(tile counters)");
+		}
+		if (prc == FLMIP_OK) {
+#ifdef FLMIP_TIMELINE
+			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 4u * 1024u;
+#else
+			const size_t n_pc = (size_t)im->layers + 2u;
+#endif
+			std::lock_guard<std::mutex> lock(ds->mtx);
+			CUresult r = CUDA_SUCCESS;
+			if (!ds->util_stream) r = cu.p_cuStreamCreate(&ds->util_stream, CU_STREAM_NON_BLOCKING);
+			if (r == CUDA_SUCCESS) r = cu.p_cuMemsetD32Async(im->pcounters, 0, n_pc, ds->util_stream);
+			if (r == CUDA_SUCCESS) r = cu.p_cuStreamSynchronize(ds->util_stream);
+			if (r != CUDA_SUCCESS) prc = cu_fail(r, "zeroing the tile counters");
+		}
+		if (prc == FLMIP_OK) {
+			im->ptile = true;
+		} else if (prc == FLMIP_ERR_OUT_OF_MEMORY) {
+			rc = prc;
+		} else {
+			if (im->wtab) cu.p_cuMemFree(im->wtab);
+			if (im->pcounters) cu.p_cuMemFree(im->pcounters);
+			im->wtab = im->pcounters = 0;
+		}
+	}
 	if (rc != FLMIP_OK) {
 		if (im->counters) cu.p_cuMemFree(im->counters);
+		if (im->wtab) cu.p_cuMemFree(im->wtab);
+		if (im->pcounters) cu.p_cuMemFree(im->pcounters);
 		if (!im->external_mem) cu.p_cuMemFree(im->mem);
 		delete im;
 		return rc;
@@ -935,6 +1186,8 @@ int flmip_image_destroy(flmip_image img) {
 		ds->images.erase(img);
 	}
 	if (img->handover) cu.p_cuEventDestroy(img->handover);
+	if (img->wtab) cu.p_cuMemFree(img->wtab);
+	if (img->pcounters) cu.p_cuMemFree(img->pcounters);
 	if (img->counters) cu.p_cuMemFree(img->counters);
 	if (img->mem && !img->external_mem) cu.p_cuMemFree(img->mem);
 	delete img;
@@ -973,7 +1226,7 @@ int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast
 	const uint32_t first_generic = img->fast ? img->fast_level_count : 1u;
 	if (img->fast) ++n;
 	if (img->tiled) {
-		n += tile_launch_count(*img, first_generic - 1u);
+		n += tile_launch_count(*img, first_generic - 1u, nullptr);
 	} else {
 		for (uint32_t l = first_generic; l < img->level_count; ++l) {
 			const flmip_level_info& li = img->levels[l];
@@ -983,6 +1236,20 @@ int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast
 	if (uses_single_pass) *uses_single_pass = img->fast ? 1u : 0u;
 	if (fast_levels) *fast_levels = img->fast ? img->fast_level_count : 0u;
 	if (launches) *launches = n;
+	return FLMIP_OK;
+}
+
+int flmip_sampler_table_entry(uint32_t g, uint32_t n, uint32_t* out) {
+	if (!out) return fail(FLMIP_ERR_INVALID, "null output");
+	if (n < 2u || g >= (n >> 1)) return fail(FLMIP_ERR_INVALID, "destination texel %u outside a level of %u >> 1 texels", g, n);
+	if (!sampler_entry(g, n, out)) return fail(FLMIP_ERR_UNSUPPORTED, "irregular sampler fetch (texel %u of a %u-texel source level)", g, n);
+	return FLMIP_OK;
+}
+
+int flmip_image_plan_tma_tile_launches(flmip_image img, uint32_t* out) {
+	if (check_image(img) || !out) return fail(FLMIP_ERR_INVALID, "null argument");
+	*out = 0;
+	if (img->tiled) tile_launch_count(*img, (img->fast ? img->fast_level_count : 1u) - 1u, out);
 	return FLMIP_OK;
 }
 
@@ -1350,12 +1617,13 @@ int flmip_batch_destroy(flmip_batch batch) {
 #ifdef FLMIP_TIMELINE
 // tuning builds only: the 4 time stamps (ns, %globaltimer) each CTA of the last single-pass launch left behind the scheduler words
 extern "C" int flmip_debug_timeline(flmip_image img, uint64_t* out, uint32_t ctas) {
-	if (check_image(img) || !out || !img->fast) return FLMIP_ERR_INVALID;
+	if (check_image(img) || !out || !(img->fast || img->ptile)) return FLMIP_ERR_INVALID;
 	WITH_DEVICE(img->device)
+	const uint64_t sched = img->fast ? img->fast_params.sched : img->pcounters + (uint64_t)img->layers * sizeof(uint32_t);
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((img->fast_params.sched + 15ull) & ~7ull), (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((sched + 15ull) & ~7ull), (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemsetD8Async(((img->fast_params.sched + 15ull) & ~7ull), 0, (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
+	CU_TRY(cu.p_cuMemsetD8Async(((sched + 15ull) & ~7ull), 0, (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
 	return FLMIP_OK;
 }
 #endif

@@ -534,6 +534,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 		if (spins > (1u << 20)) __trap();
 	}
 }
+// Tuning alternative (-DFLMIP_FINISHER_SLEEP_WAIT) for waits that last about as long as a whole tile (the finisher pool waiting for its
+// next cascade slot): the hardware-suspended try_wait above comes back every few dozen nanoseconds (ncu: ~100 trips of 6 instructions per
+// wait, 8 % of all issued instructions of the persistent tile kernel); polling with an explicit sleep removes those instructions.
+// Measured: no gain (N2 0.3219 vs 0.3218 ms, C3 slightly worse) -- the issue slots were not what the consumers lacked; not the default.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+	for (uint32_t spins = 0;; ++spins) {
+		uint32_t done;
+		asm volatile(
+			"{\n\t"
+			".reg .pred p;\n\t"
+			"mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t"
+			"}"
+			: "=r"(done)
+			: "r"(smem_u32(bar)), "r"(parity)
+			: "memory");
+		if (done) return;
+		__nanosleep(128);
+		if (spins > (1u << 24)) __trap();
+	}
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
 					 smem_u32(dst)),
@@ -656,6 +677,19 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v
 	uint32_t old;
 	asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
 	return old;
+}
+// the same with `count` arrivals at once (a unit of tiles that one CTA joined in shared memory)
+__device__ __forceinline__ bool arrive_last_n(uint32_t* counter, uint32_t count, uint32_t expected, uint32_t lane) {
+	__syncwarp();
+	uint32_t last = 0;
+	if (lane == 0) {
+		const uint32_t old = atom_add_acq_rel_gpu(counter, count);
+		last = (old + count == expected);
+		if (last) *counter = 0u;
+	}
+	last = __shfl_sync(0xFFFFFFFFu, last, 0);
+	__syncwarp();
+	return last != 0;
 }
 __device__ __forceinline__ bool arrive_last(uint32_t* counter, uint32_t expected, uint32_t lane) {
 	__syncwarp();
@@ -839,7 +873,11 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 			n = __shfl_sync(0xFFFFFFFFu, n, 0);
 			const uint32_t slot = n % FLMIP_FINISHER_WARPS, use = n / FLMIP_FINISHER_WARPS;
 			uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
+#ifdef FLMIP_FINISHER_SLEEP_WAIT
+			mbar_wait_sleep(&slot_full[slot], use & 1u);
+#else
 			mbar_wait(&slot_full[slot], use & 1u);
+#endif
 			const uint32_t t = slot_tile[slot];
 			if (t == FLMIP_NO_TILE) break; // the consumers are done: one sentinel per finisher warp
 			const TileCoord tc = tile_coord<DIMS>(P, t);
@@ -1512,6 +1550,654 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------
+// persistent TMA tile kernel (flmip_ptile2d_*): any 2D image whose source rows are 16-byte multiples.
+//
+// The CTA structure of the single-pass kernel (TMA ring, producer warp with the dynamic scheduler, 8 consumer warps that hold
+// a 512 B x 64 row tile in registers and produce levels 1 and 2 from it, a pool of finisher warps for the rest of the tile,
+// the last tile of a layer finishes the chain in the same launch) with the reference's GENERAL sampler arithmetic
+// (host_image.hpp:869-894): along each axis the fetch for destination texel g reads texels {2g, 2g + 1} of the previous level
+// in the roles A (neighbour) and B (active texel) with a weight t = 0.5 +- eps of B, out = (B - A) * t + A, x first, then y.
+// Roles and weights come from the image's sampler table (flmip_ptile_params), computed once per image on the host with the
+// reference's float32 operations.  Partial tiles at the image border: TMA fills what lies outside with zeros, stores are masked.
+// Levels 1 and 2 (in registers) assume A, B in {2g, 2g + 1}; the host only selects this kernel when the texel-2 fetch of the
+// reference (see axis_fetch) cannot occur there.  From level 3 on texels are addressed by index and the fetch is honoured.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float wt_weight(uint32_t e) { return __uint_as_float(e & 0x3FFFFFFFu); }
+__device__ __forceinline__ uint32_t wt_swap(uint32_t e) { return e >> 31; }
+
+// (b - a) * t + a on pairs, product and sum rounded separately (t is not 0.5: the product is inexact)
+__device__ __forceinline__ f32x2_t lerp2_t(f32x2_t a, f32x2_t b, f32x2_t t) { return add2_rn(mul2_sep(sub2_rn(b, a), t), a); }
+
+// Puts texel A of every x pair of a 16-byte chunk into the even slot and texel B into the odd one (e[i]: table entry of pair i).
+template <int BPP> __device__ __forceinline__ void preswap_chunk(uint32_t (&w)[4], const uint32_t (&e)[8 / BPP]) {
+	static_assert(BPP <= 8, "16-byte texels swap whole chunks");
+	if constexpr (BPP == 8) {
+		const bool s = (int)e[0] < 0;
+		const uint32_t a0 = s ? w[2] : w[0], a1 = s ? w[3] : w[1], b0 = s ? w[0] : w[2], b1 = s ? w[1] : w[3];
+		w[0] = a0; w[1] = a1; w[2] = b0; w[3] = b1;
+	} else if constexpr (BPP == 4) {
+#pragma unroll
+		for (int p = 0; p < 2; ++p) {
+			const bool s = (int)e[p] < 0;
+			const uint32_t a = s ? w[2 * p + 1] : w[2 * p], b = s ? w[2 * p] : w[2 * p + 1];
+			w[2 * p] = a; w[2 * p + 1] = b;
+		}
+	} else if constexpr (BPP == 2) {
+#pragma unroll
+		for (int p = 0; p < 4; ++p) w[p] = __byte_perm(w[p], 0u, (int)e[p] < 0 ? 0x1032u : 0x3210u);
+	} else {
+#pragma unroll
+		for (int p = 0; p < 4; ++p) {
+			const uint32_t selector = 0x3210u ^ ((int)e[2 * p] < 0 ? 0x0011u : 0u) ^ ((int)e[2 * p + 1] < 0 ? 0x1100u : 0u);
+			w[p] = __byte_perm(w[p], 0u, selector);
+		}
+	}
+}
+
+// rows rA / rB (NW words of whole texels, A in the even slot of every x pair) -> NW / 2 words of the next level;
+// tx[j] = weight of output texel j along x, ty = weight along y
+template <uint32_t EK, int CH, int NW>
+__device__ __forceinline__ void reduce_rows_2d_t(const uint32_t (&rA)[NW], const uint32_t (&rB)[NW],
+												 const float (&tx)[(NW * 2 / Codec<EK>::BYTES) / CH > 0 ? (NW * 2 / Codec<EK>::BYTES) / CH : 1], float ty,
+												 uint32_t (&out)[NW / 2], uint32_t no_double) {
+	using C = Codec<EK>;
+	constexpr int NO = NW * 2 / C::BYTES;
+	static_assert(NO >= CH && (NO % CH) == 0, "row must hold at least one x pair");
+	if constexpr (!C::IS_INT) {
+		static_assert((NO % 2) == 0, "pairs of output elements");
+		f32x2_t v[NO / 2];
+		const f32x2_t ty2 = splat2(ty);
+#pragma unroll
+		for (int p = 0; p < NO / 2; ++p) {
+			const int e0 = 2 * p, e1 = 2 * p + 1;
+			const int ea0 = (2 * (e0 / CH)) * CH + (e0 % CH), eb0 = ea0 + CH, ea1 = (2 * (e1 / CH)) * CH + (e1 % CH), eb1 = ea1 + CH;
+			const f32x2_t tx2 = pk2(__float_as_uint(tx[e0 / CH]), __float_as_uint(tx[e1 / CH]));
+			const f32x2_t x0 = lerp2_t(C::dec2_at(rA, ea0, ea1), C::dec2_at(rA, eb0, eb1), tx2);
+			const f32x2_t x1 = lerp2_t(C::dec2_at(rB, ea0, ea1), C::dec2_at(rB, eb0, eb1), tx2);
+			v[p] = lerp2_t(x0, x1, ty2);
+		}
+		C::template enc_pack2<NO / 2>(v, out, no_double);
+	} else {
+		uint32_t v[NO];
+#pragma unroll
+		for (int e = 0; e < NO; ++e) {
+			const int ea = (2 * (e / CH)) * CH + (e % CH), eb = ea + CH;
+			const uint32_t x0 = C::lerp_t(C::dec_at(rA, ea), C::dec_at(rA, eb), tx[e / CH]);
+			const uint32_t x1 = C::lerp_t(C::dec_at(rB, ea), C::dec_at(rB, eb), tx[e / CH]);
+			v[e] = C::lerp_t(x0, x1, ty);
+		}
+		C::template enc_pack<NO>(v, out, no_double);
+	}
+}
+
+struct PRegion {
+	uint32_t w, h;   // nominal texels of the region at level `lvl` (what lies outside the image is garbage and never read)
+	uint32_t ox, oy; // origin in level-`lvl` texel coordinates
+	uint32_t lvl;
+};
+
+template <int BPP> __device__ __forceinline__ uint8_t* plevel_layer_ptr(const flmip_ptile_params& P, uint32_t level, uint32_t layer) {
+	return reinterpret_cast<uint8_t*>(P.base) + P.level_off[level] + (uint64_t)layer * ((uint64_t)P.dim[level][0] * P.dim[level][1] * BPP);
+}
+
+// One full warp: reduces the dense region `src` (row pitch R.w texels) level by level up to `stop_level`, or until the region
+// cannot be halved any more; every level is written to global memory and re-read from its stored bits.  Texels are fetched by
+// index, so the texel-2 fetch of the reference is honoured (the host guarantees it stays inside the region).
+// The sampler entries are staged in `scratch` first (a dependent round trip to L2 per texel would serialise the warp):
+// TILE_STAGE (region of a tile, power-of-two extents): the entries of ALL levels with one batch of loads -- needs R.w + R.h words;
+// otherwise (whole level of a layer, any extents): level by level, as far as `cap` words reach.
+template <uint32_t EK, int CH, bool TILE_STAGE>
+__device__ __forceinline__ void pcascade_warp(uint8_t*& src, uint8_t*& dst, PRegion& R, const flmip_ptile_params& P, uint32_t layer, uint32_t lane,
+											  uint32_t stop_level, uint32_t* scratch, uint32_t cap) {
+	using C = Codec<EK>;
+	constexpr int BPP = C::BYTES * CH;
+	using IO = TexelIO<BPP>;
+	constexpr int NW = IO::NW;
+	const uint32_t* const wtab = reinterpret_cast<const uint32_t*>(P.wtab);
+	if constexpr (TILE_STAGE) {
+		uint32_t w = R.w, h = R.h, lvl = R.lvl, ox = R.ox, oy = R.oy, bx = 0, by = R.w;
+		while (lvl < stop_level && w >= 2 && h >= 2) {
+			w >>= 1; h >>= 1; ox >>= 1; oy >>= 1; ++lvl;
+			// (entries past the level's extent exist: every table segment is padded by more than a tile)
+#if defined(FLMIP_PT_EXP_FIN) && FLMIP_PT_EXP_FIN == 2
+			for (uint32_t i = lane; i < w; i += 32) scratch[bx + i] = 0x3F000000u;
+			for (uint32_t i = lane; i < h; i += 32) scratch[by + i] = 0x3F000000u;
+#else
+			for (uint32_t i = lane; i < w; i += 32) scratch[bx + i] = __ldg(wtab + P.wtab_off[lvl][0] + ox + i);
+			for (uint32_t i = lane; i < h; i += 32) scratch[by + i] = __ldg(wtab + P.wtab_off[lvl][1] + oy + i);
+#endif
+			bx += w; by += h;
+		}
+		__syncwarp();
+	}
+	uint32_t bx = 0, by = R.w;
+	while (R.lvl < stop_level && R.w >= 2 && R.h >= 2) {
+		const uint32_t L = R.lvl + 1;
+		const uint32_t dw = R.w >> 1, dh = R.h >> 1;
+		const uint32_t LW = P.dim[L][0], LH = P.dim[L][1];
+		const uint32_t ox = R.ox >> 1, oy = R.oy >> 1;
+		uint8_t* const gdst = plevel_layer_ptr<BPP>(P, L, layer);
+		const uint32_t* const tabx = wtab + P.wtab_off[L][0] + ox;
+		const uint32_t* const taby = wtab + P.wtab_off[L][1] + oy;
+		bool staged = TILE_STAGE;
+		if constexpr (!TILE_STAGE) {
+			staged = dw + dh <= cap;
+			if (staged) {
+				bx = 0; by = dw;
+				for (uint32_t i = lane; i < dw; i += 32) scratch[i] = __ldg(tabx + i);
+				for (uint32_t i = lane; i < dh; i += 32) scratch[dw + i] = __ldg(taby + i);
+				__syncwarp();
+			}
+		}
+		const uint32_t sw = 31u - __clz(dw);
+		for (uint32_t i = lane; i < dw * dh; i += 32) {
+			uint32_t x, y;
+			if constexpr (TILE_STAGE) { x = i & (dw - 1u); y = i >> sw; }
+			else { y = i / dw; x = i - y * dw; }
+			const uint32_t gx = ox + x, gy = oy + y;
+			if (gx < LW && gy < LH) {
+				const uint32_t ex = staged ? scratch[bx + x] : __ldg(tabx + x), ey = staged ? scratch[by + y] : __ldg(taby + y);
+				// texel indices inside the region: A / B = {2g, 2g + 1} in either order, or (2, 0) for the texel-2 fetch at g = 0
+				const uint32_t lx[2] = { 2u * x + ((ex & FLMIP_WTAB_TEXEL2) ? 2u : wt_swap(ex)), 2u * x + ((ex & FLMIP_WTAB_TEXEL2) ? 0u : 1u - wt_swap(ex)) };
+				const uint32_t ly[2] = { 2u * y + ((ey & FLMIP_WTAB_TEXEL2) ? 2u : wt_swap(ey)), 2u * y + ((ey & FLMIP_WTAB_TEXEL2) ? 0u : 1u - wt_swap(ey)) };
+				uint32_t raw[4][NW];
+#pragma unroll
+				for (int b = 0; b < 4; ++b) IO::template load<false>(src + ((size_t)ly[b >> 1] * R.w + lx[b & 1]) * BPP, raw[b]);
+				axis_f af[2];
+				af[0].t = wt_weight(ex);
+				af[1].t = wt_weight(ey);
+				uint32_t out[NW];
+				tile_reduce_block<EK, CH, 2, NW>(raw, af, P.no_double, out);
+				IO::store(dst + (size_t)i * BPP, out);
+				IO::store(gdst + ((uint64_t)gy * LW + gx) * BPP, out);
+			}
+		}
+		__syncwarp();
+		uint8_t* t = src; src = dst; dst = t;
+		R.w = dw; R.h = dh; R.ox = ox; R.oy = oy; R.lvl = L;
+		if constexpr (TILE_STAGE) { bx += dw; by += dh; }
+	}
+}
+
+// tile coordinates that ride along with a stage / a cascade slot
+struct PTile {
+	uint32_t x, y, layer, pad;
+};
+
+template <uint32_t EK, int CH>
+__device__ __forceinline__ void ptile_body(const CUtensorMap& tmap, const flmip_ptile_params& P) {
+	using C = Codec<EK>;
+	constexpr int BPP = C::BYTES * CH;
+	using TL = flmip_tiling<BPP, 2>;
+	using IO = TexelIO<BPP>;
+	constexpr bool WIDE = (BPP == 16);
+	constexpr int ROW_BYTES = TL::TILE_BYTES_X;
+	constexpr int NPAIR = WIDE ? 1 : 8 / BPP;          // x pairs per 16-byte chunk (16-byte texels: one pair per thread)
+	static_assert(TL::THREADS == FLMIP_CONSUMER_THREADS, "one consumer thread per 32 B x 4 rows");
+
+	// [stages x tile][FLMIP_FINISHER_WARPS cascade slots (buf_a, buf_b)][patch (gathered level of one layer)][patch / 4]
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	__shared__ uint64_t full_bar[FLMIP_MAX_STAGES], empty_bar[FLMIP_MAX_STAGES];
+	__shared__ uint64_t slot_full[FLMIP_FINISHER_WARPS], slot_empty[FLMIP_FINISHER_WARPS];
+	__shared__ uint32_t finisher_ticket, patch_lock, unit_count[2];
+	__shared__ uint32_t stage_tile[FLMIP_MAX_STAGES], slot_tile[FLMIP_FINISHER_WARPS];
+	__shared__ __align__(16) PTile stage_pos[FLMIP_MAX_STAGES], slot_pos[FLMIP_FINISHER_WARPS];
+	__shared__ __align__(16) uint64_t stage_org[FLMIP_MAX_STAGES][2]; // the tile's part of level src + 1 / src + 2 in global memory
+	// sampler entries staged by the finisher warps: tile stage (TX / 4 + TY / 4 <= 144 words per warp), last-tile stage (one level at a time)
+	__shared__ uint32_t fin_tab[FLMIP_FINISHER_WARPS][160];
+	__shared__ uint32_t tail_tab[FLMIP_PTILE_TAIL_TAB];
+	static_assert(TL::TX / 4 + TL::TY / 4 <= 160, "tile-stage sampler entries");
+	const uint32_t stages = P.stages;
+	uint8_t* const cascade_base = smem_raw + (size_t)stages * TL::TILE_BYTES;
+	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t S = P.src_level;
+
+	if (tid == 0) {
+		finisher_ticket = 0;
+		patch_lock = 0;
+		unit_count[0] = unit_count[1] = 0;
+		for (uint32_t s = 0; s < stages; ++s) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], FLMIP_CONSUMER_WARPS);
+		}
+		for (uint32_t f = 0; f < FLMIP_FINISHER_WARPS; ++f) {
+			mbar_init(&slot_full[f], FLMIP_CONSUMER_WARPS);
+			mbar_init(&slot_empty[f], 1);
+		}
+		fence_mbar_init();
+	}
+	__syncthreads();
+	pdl_wait_then_release();
+	if (tid == 0) FLMIP_STAMP(P, 0); // CTA may touch global memory from here
+
+	// the finisher pool is idle when the consumers' in-register levels end the launch
+#ifdef FLMIP_PT_EXP_NOFIN
+	const bool need_finish = false; // tuning experiment: the chain stops after the consumers' two levels
+#else
+	const bool need_finish = P.last_level > S + 2u;
+#endif
+	const uint32_t tiles_per_layer = P.tiles[0] * P.tiles[1];
+
+	if (warp >= FLMIP_FINISHER_WARP0) {
+		// ---- finishers: levels src + 3 .. tile_last of a tile, then (last tile of a layer) the rest of the chain ----------
+		if (!need_finish) return;
+		uint8_t* const patch_a = cascade_base + FLMIP_FINISHER_WARPS * SLOT_BYTES;
+		uint8_t* const patch_b = patch_a + FLMIP_PTILE_PATCH_BYTES;
+		for (;;) {
+			uint32_t n = 0;
+			if (lane == 0) n = atomicAdd(&finisher_ticket, 1u);
+			n = __shfl_sync(0xFFFFFFFFu, n, 0);
+			const uint32_t slot = n % FLMIP_FINISHER_WARPS, use = n / FLMIP_FINISHER_WARPS;
+			uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
+#ifdef FLMIP_FINISHER_SLEEP_WAIT
+			mbar_wait_sleep(&slot_full[slot], use & 1u);
+#else
+			mbar_wait(&slot_full[slot], use & 1u);
+#endif
+			const uint32_t t = slot_tile[slot];
+			if (t == FLMIP_NO_TILE) break;
+			const PTile tc = slot_pos[slot];
+			PRegion R;
+			R.lvl = S + 2u;
+			R.w = TL::TX >> 2; R.h = TL::TY >> 2;
+			R.ox = tc.x * R.w; R.oy = tc.y * R.h;
+			uint8_t *src = buf_a, *dst = buf_a + TL::CASCADE_BYTES;
+#if !defined(FLMIP_PT_EXP_FIN) || FLMIP_PT_EXP_FIN != 1
+			pcascade_warp<EK, CH, true>(src, dst, R, P, tc.layer, lane, P.tile_last, fin_tab[warp - FLMIP_FINISHER_WARP0], 160u);
+#endif
+			__syncwarp();
+#ifdef FLMIP_PT_EXP_FIN
+			// tuning experiments: 1 = the slot is handed back at once, 2 / 3 = tile stage only (constant / real sampler entries), no publish
+			if (lane == 0) mbar_arrive(&slot_empty[slot]);
+			continue;
+#endif
+			// Publishing a tile costs a release fence + an atomic round trip (microseconds under load): with many tiles per CTA the pool
+			// cannot keep up (N2: 0.32 ms against 0.20 ms without finishers).  The tiles of a unit (4 consecutive tile indices, always
+			// worked through by one CTA in ring order) therefore meet at a counter in shared memory and whoever brings the last one
+			// publishes all of them at once.  Two counters suffice: a slot is only released after its tile has been counted, and
+			// FLMIP_FINISHER_WARPS <= tiles per unit (see fast_body).
+			bool publish = true;
+			uint32_t t0 = t, n_pub = 1u;
+			if (P.unit_shift != 0u && P.last_level > P.tile_last) {
+				const uint32_t U = 1u << P.unit_shift;
+				t0 = t & ~(U - 1u);
+				n_pub = min(U, P.total_tiles - t0);
+				const uint32_t q = (n >> P.unit_shift) & 1u;
+				uint32_t last = 0;
+				if (lane == 0) {
+					__threadfence_block();
+					last = (atomicAdd(&unit_count[q], 1u) == n_pub - 1u);
+					if (last) {
+						unit_count[q] = 0u;
+						__threadfence_block();
+					}
+				}
+				publish = __shfl_sync(0xFFFFFFFFu, last, 0) != 0;
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_empty[slot]); // the slot is free again before the slow part starts
+			if (P.last_level <= P.tile_last || !publish) continue;
+			// the last tile of a layer gathers level tile_last of the layer and finishes the chain (a unit may span layers)
+			const uint32_t layer_a = t0 / tiles_per_layer, layer_b = (t0 + n_pub - 1u) / tiles_per_layer;
+			for (uint32_t layer = layer_a; layer <= layer_b; ++layer) {
+				const uint32_t lo = max(t0, layer * tiles_per_layer), hi = min(t0 + n_pub, (layer + 1u) * tiles_per_layer);
+				if (!arrive_last_n(reinterpret_cast<uint32_t*>(P.counters) + layer, hi - lo, tiles_per_layer, lane)) continue;
+				if (lane == 0) {
+					while (atomicCAS(&patch_lock, 0u, 1u) != 0u) __nanosleep(64);
+				}
+				__syncwarp();
+				PRegion G;
+				G.lvl = P.tile_last;
+				G.w = P.dim[G.lvl][0]; G.h = P.dim[G.lvl][1];
+				G.ox = G.oy = 0;
+				// one layer of a level is contiguous in global memory: a linear copy, loads batched (a round trip to L2 costs microseconds
+				// under load): 16 bytes per lane and load where the layer starts on a 16-byte boundary, 8 loads in flight
+				{
+					constexpr uint32_t U = (IO::NW >= 4 ? 2u : (IO::NW == 2 ? 4u : 8u));
+					const uint8_t* const g = plevel_layer_ptr<BPP>(P, G.lvl, layer);
+					const uint32_t ntex = G.w * G.h;
+					uint32_t first = 0; // texels already copied by the vector part
+					if ((reinterpret_cast<uint64_t>(g) & 15u) == 0u) {
+						const uint32_t n16 = (uint32_t)(((uint64_t)ntex * BPP) >> 4);
+						for (uint32_t b0 = 0; b0 < n16; b0 += 32u * 8u) {
+							uint4 v[8];
+#pragma unroll
+							for (uint32_t u = 0; u < 8u; ++u) {
+								const uint32_t i = b0 + u * 32u + lane;
+								if (i < n16) v[u] = __ldcg(reinterpret_cast<const uint4*>(g) + i);
+							}
+#pragma unroll
+							for (uint32_t u = 0; u < 8u; ++u) {
+								const uint32_t i = b0 + u * 32u + lane;
+								if (i < n16) reinterpret_cast<uint4*>(patch_a)[i] = v[u];
+							}
+						}
+						first = (uint32_t)(((uint64_t)n16 << 4) / BPP);
+					}
+					for (uint32_t b0 = first; b0 < ntex; b0 += 32u * U) {
+						uint32_t t[U][IO::NW];
+#pragma unroll
+						for (uint32_t u = 0; u < U; ++u) {
+							const uint32_t i = b0 + u * 32u + lane;
+							if (i < ntex) IO::template load<true>(g + (size_t)i * BPP, t[u]);
+						}
+#pragma unroll
+						for (uint32_t u = 0; u < U; ++u) {
+							const uint32_t i = b0 + u * 32u + lane;
+							if (i < ntex) IO::store(patch_a + (size_t)i * BPP, t[u]);
+						}
+					}
+					__syncwarp();
+				}
+				uint8_t *ps = patch_a, *pd = patch_b;
+				pcascade_warp<EK, CH, false>(ps, pd, G, P, layer, lane, P.last_level, tail_tab, FLMIP_PTILE_TAIL_TAB);
+				__syncwarp();
+				if (lane == 0) {
+					__threadfence_block();
+					atomicExch(&patch_lock, 0u);
+				}
+			}
+		}
+		if (lane == 0) FLMIP_STAMP_MAX(P, 3); // last finisher warp of the CTA done
+		return;
+	}
+	if (warp == FLMIP_PRODUCER_WARP) {
+		// ---- producer: dynamic tile scheduler + TMA issue (see fast_body) -------------------------------------------------
+		const uint32_t PF = FLMIP_SCHED_PREFETCH;
+		uint32_t* const sched = reinterpret_cast<uint32_t*>(P.sched);
+		uint32_t pf = FLMIP_NO_TILE;
+		if (lane == 0) pf = blockIdx.x;
+		else if (lane < PF) pf = gridDim.x + atomicAdd(&sched[0], 1u);
+		uint32_t s = 0, use = 0, dead = 0;
+		const uint64_t p1 = (uint64_t)P.dim[S + 1u][0] * BPP;
+		const uint64_t p2 = (P.last_level >= S + 2u) ? (uint64_t)P.dim[S + 2u][0] * BPP : 0ull;
+		const uint32_t U = 1u << P.unit_shift, total_units = (P.total_tiles + U - 1u) >> P.unit_shift;
+		for (uint32_t it = 0; dead < PF; ++it) {
+			const uint32_t u = __shfl_sync(0xFFFFFFFFu, pf, it % PF);
+			if (u >= total_units) { ++dead; continue; }
+			dead = 0;
+			if (lane == it % PF) pf = gridDim.x + atomicAdd(&sched[0], 1u);
+			for (uint32_t k = 0; k < U; ++k) {
+			const uint32_t t = (u << P.unit_shift) + k;
+			if (t >= P.total_tiles) break;
+			if (lane == 0) {
+				if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
+				PTile tc;
+				tc.x = t % P.tiles[0];
+				const uint32_t r = t / P.tiles[0];
+				tc.y = r % P.tiles[1];
+				tc.layer = r / P.tiles[1];
+				tc.pad = 0;
+				mbar_expect_tx(&full_bar[s], TL::TILE_BYTES);
+				tma_load_3d(smem_raw + (size_t)s * TL::TILE_BYTES, &tmap, &full_bar[s], (int)(tc.x * (ROW_BYTES / 4)), (int)(tc.y * TL::TY), (int)tc.layer);
+				stage_tile[s] = t;
+				stage_pos[s] = tc;
+				stage_org[s][0] = reinterpret_cast<uint64_t>(plevel_layer_ptr<BPP>(P, S + 1u, tc.layer)) + (uint64_t)tc.y * (TL::TY / 2) * p1 + (uint64_t)tc.x * (ROW_BYTES / 2);
+				stage_org[s][1] = (P.last_level >= S + 2u)
+									  ? reinterpret_cast<uint64_t>(plevel_layer_ptr<BPP>(P, S + 2u, tc.layer)) + (uint64_t)tc.y * (TL::TY / 4) * p2 + (uint64_t)tc.x * (ROW_BYTES / 4)
+									  : 0ull;
+				mbar_arrive(&full_bar[s]);
+			}
+			if (++s == stages) { s = 0; ++use; }
+			}
+			__syncwarp();
+		}
+		if (lane == 0) {
+			FLMIP_STAMP(P, 1); // the scheduler ran dry for this CTA: all of its loads are issued
+			if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
+			stage_tile[s] = FLMIP_NO_TILE;
+			mbar_arrive(&full_bar[s]);
+			__threadfence();
+			if (atomicAdd(&sched[1], 1u) == gridDim.x - 1u) {
+				sched[0] = 0u;
+				sched[1] = 0u;
+			}
+		}
+		return;
+	}
+
+	// ---- consumers: thread = 2 chunks (32 B) x 4 rows of the tile -> 16 B x 2 rows of level 1 -> 8 B of level 2 -----------
+	const uint32_t* const wtab = reinterpret_cast<const uint32_t*>(P.wtab);
+	const uint32_t* const tab1x = wtab + P.wtab_off[S + 1u][0];
+	const uint32_t* const tab1y = wtab + P.wtab_off[S + 1u][1];
+	const bool has_l2 = P.last_level >= S + 2u;
+	const uint32_t* const tab2x = wtab + P.wtab_off[has_l2 ? S + 2u : S + 1u][0];
+	const uint32_t* const tab2y = wtab + P.wtab_off[has_l2 ? S + 2u : S + 1u][1];
+	const uint32_t W1 = P.dim[S + 1u][0], H1 = P.dim[S + 1u][1];
+	const uint32_t W2 = has_l2 ? P.dim[S + 2u][0] : 0u, H2 = has_l2 ? P.dim[S + 2u][1] : 0u;
+	const uint64_t pitch1 = (uint64_t)W1 * BPP, pitch2 = (uint64_t)W2 * BPP;
+	const bool vec1 = P.vec1 != 0u; // 16-byte stores of level 1 (else two of 8 bytes: rows start on 8-byte boundaries)
+	const bool vec2 = P.vec2 != 0u; // 8-byte stores of level 2 (else two of 4 bytes)
+	const uint32_t sel = (lane >> 2) & 1u; // quarter-warps read conflict-free by swapping the chunk order on lane bit 2
+	const uint32_t tx = tid % TL::THREADS_X, ty = tid / TL::THREADS_X;
+	uint32_t s = 0, use = 0, slot = 0, slot_use = 0;
+	for (;;) {
+		mbar_wait(&full_bar[s], use & 1u);
+		const uint32_t t = stage_tile[s];
+		if (t == FLMIP_NO_TILE) {
+			if (tid == 0) FLMIP_STAMP(P, 2); // consumers saw the sentinel
+			break;
+		}
+		const uint8_t* const tile = smem_raw + (size_t)s * TL::TILE_BYTES;
+		uint8_t* const buf_a = cascade_base + slot * SLOT_BYTES;
+		const PTile tc = stage_pos[s];
+		const ulonglong2 org = *reinterpret_cast<const ulonglong2*>(stage_org[s]);
+		uint8_t* const g1 = reinterpret_cast<uint8_t*>(org.x);
+		uint8_t* const g2 = reinterpret_cast<uint8_t*>(org.y);
+
+		// sampler entries of this thread's texels (L1-resident: every thread of a tile column / row reads the same ones).
+		// Level 1: rows 2 ty, 2 ty + 1; columns of the two chunks the thread reads (physical order k ^ sel).  Level 2: row ty.
+		uint32_t ey1[2], ex1[2][NPAIR], ey2 = 0, ex2[NPAIR];
+#ifdef FLMIP_PT_EXP_NOTAB
+		// tuning experiment: constant entries instead of the table
+		ey1[0] = ey1[1] = ey2 = 0x3F000000u;
+#pragma unroll
+		for (int i = 0; i < NPAIR; ++i) ex1[0][i] = ex1[1][i] = ex2[i] = 0x3F000000u;
+		if (false)
+#endif
+		{
+			const uint32_t gy1 = tc.y * (TL::TY / 2) + 2u * ty;
+			ey1[0] = __ldg(tab1y + gy1);
+			ey1[1] = __ldg(tab1y + gy1 + 1u);
+			if constexpr (!WIDE) {
+#pragma unroll
+				for (int k = 0; k < 2; ++k)
+#pragma unroll
+					for (int i = 0; i < NPAIR; ++i) ex1[k][i] = __ldg(tab1x + tc.x * (TL::TX / 2) + (2u * tx + ((uint32_t)k ^ sel)) * NPAIR + i);
+#pragma unroll
+				for (int i = 0; i < NPAIR; ++i) ex2[i] = has_l2 ? __ldg(tab2x + tc.x * (TL::TX / 4) + tx * NPAIR + i) : 0u;
+			} else {
+				ex1[0][0] = ex1[1][0] = __ldg(tab1x + tc.x * (TL::TX / 2) + tx);
+				ex2[0] = has_l2 ? __ldg(tab2x + tc.x * (TL::TX / 4) + (tx >> 1)) : 0u;
+			}
+			if (has_l2) ey2 = __ldg(tab2y + tc.y * (TL::TY / 4) + ty);
+		}
+
+		// rows in their roles: level-1 row j reads tile rows 4 ty + 2 j + {0, 1}; A is the second one when the roles are swapped
+		uint32_t rawA[2][2][4], rawB[2][2][4]; // [level-1 row][chunk][word]
+#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			const uint32_t sy = wt_swap(ey1[j]);
+			const uint8_t* const rowA = tile + (4u * ty + 2u * j + sy) * ROW_BYTES;
+			const uint8_t* const rowB = tile + (4u * ty + 2u * j + 1u - sy) * ROW_BYTES;
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				const uint4 a = *reinterpret_cast<const uint4*>(rowA + (2 * tx + (k ^ sel)) * 16);
+				const uint4 b = *reinterpret_cast<const uint4*>(rowB + (2 * tx + (k ^ sel)) * 16);
+				rawA[j][k][0] = a.x; rawA[j][k][1] = a.y; rawA[j][k][2] = a.z; rawA[j][k][3] = a.w;
+				rawB[j][k][0] = b.x; rawB[j][k][1] = b.y; rawB[j][k][2] = b.z; rawB[j][k][3] = b.w;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty_bar[s]); // the tile lives in registers: hand the stage back
+
+		uint32_t l1[2][4]; // two level-1 rows of 16 bytes, logical (left, right) order
+		if constexpr (!WIDE) {
+			float tx1[2][NPAIR];
+			uint32_t any1 = 0;
+#pragma unroll
+			for (int k = 0; k < 2; ++k)
+#pragma unroll
+				for (int i = 0; i < NPAIR; ++i) {
+					tx1[k][i] = wt_weight(ex1[k][i]);
+					any1 |= ex1[k][i];
+				}
+			// most tiles of most sizes have no swapped x roles at all (1920: none, 1080: every fifth column): skip the selects then
+#ifdef FLMIP_PT_NO_SELSKIP
+			any1 = 0x80000000u;
+#endif
+			if (__any_sync(0xFFFFFFFFu, (int)any1 < 0)) {
+#pragma unroll
+				for (int j = 0; j < 2; ++j)
+#pragma unroll
+					for (int k = 0; k < 2; ++k) {
+						preswap_chunk<BPP>(rawA[j][k], ex1[k]);
+						preswap_chunk<BPP>(rawB[j][k], ex1[k]);
+					}
+			}
+#pragma unroll
+			for (int j = 0; j < 2; ++j) {
+				uint32_t o[2][2];
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					reduce_rows_2d_t<EK, CH, 4>(rawA[j][k], rawB[j][k], tx1[k], wt_weight(ey1[j]), o[k], P.no_double);
+				}
+				l1[j][0] = sel ? o[1][0] : o[0][0]; l1[j][1] = sel ? o[1][1] : o[0][1];
+				l1[j][2] = sel ? o[0][0] : o[1][0]; l1[j][3] = sel ? o[0][1] : o[1][1];
+			}
+		} else {
+			// 16-byte texels: the thread's two chunks are texels 2 tx and 2 tx + 1; chunk k holds texel k ^ sel, A is texel `swap`
+			const uint32_t pick = sel ^ wt_swap(ex1[0][0]);
+			const float tx1[1] = { wt_weight(ex1[0][0]) };
+#pragma unroll
+			for (int j = 0; j < 2; ++j) {
+				uint32_t ra[8], rb[8];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					ra[i] = pick ? rawA[j][1][i] : rawA[j][0][i];
+					ra[4 + i] = pick ? rawA[j][0][i] : rawA[j][1][i];
+					rb[i] = pick ? rawB[j][1][i] : rawB[j][0][i];
+					rb[4 + i] = pick ? rawB[j][0][i] : rawB[j][1][i];
+				}
+				reduce_rows_2d_t<EK, CH, 8>(ra, rb, tx1, wt_weight(ey1[j]), l1[j], P.no_double);
+			}
+		}
+		// level 1: 16 bytes per row, masked at the image border
+		{
+			const uint32_t xb = tc.x * (ROW_BYTES / 2) + tx * 16u; // byte offset in the level-1 row
+			const uint32_t gy = tc.y * (TL::TY / 2) + 2u * ty;
+#pragma unroll
+			for (int j = 0; j < 2; ++j) {
+				if (gy + j < H1 && xb < pitch1) {
+					uint8_t* const p = g1 + (uint64_t)(2u * ty + j) * pitch1 + tx * 16u;
+					if (vec1) {
+						*reinterpret_cast<uint4*>(p) = make_uint4(l1[j][0], l1[j][1], l1[j][2], l1[j][3]);
+					} else if constexpr (!WIDE) {
+						*reinterpret_cast<uint2*>(p) = make_uint2(l1[j][0], l1[j][1]);
+						if (xb + 8u < pitch1) *reinterpret_cast<uint2*>(p + 8) = make_uint2(l1[j][2], l1[j][3]);
+					}
+				}
+			}
+		}
+		if (has_l2) {
+			const float ty2 = wt_weight(ey2);
+			const uint32_t sy2 = wt_swap(ey2);
+			if constexpr (!WIDE) {
+				uint32_t ra[4], rb[4], l2[2];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					ra[i] = sy2 ? l1[1][i] : l1[0][i];
+					rb[i] = sy2 ? l1[0][i] : l1[1][i];
+				}
+				float tx2[NPAIR];
+				uint32_t any2 = 0;
+#pragma unroll
+				for (int i = 0; i < NPAIR; ++i) {
+					tx2[i] = wt_weight(ex2[i]);
+					any2 |= ex2[i];
+				}
+#ifdef FLMIP_PT_NO_SELSKIP
+				any2 = 0x80000000u;
+#endif
+				if (__any_sync(0xFFFFFFFFu, (int)any2 < 0)) {
+					preswap_chunk<BPP>(ra, ex2);
+					preswap_chunk<BPP>(rb, ex2);
+				}
+				reduce_rows_2d_t<EK, CH, 4>(ra, rb, tx2, ty2, l2, P.no_double);
+				const uint32_t xb = tc.x * (ROW_BYTES / 4) + tx * 8u;
+				if (tc.y * (TL::TY / 4) + ty < H2 && xb < pitch2) {
+					uint8_t* const p = g2 + (uint64_t)ty * pitch2 + tx * 8u;
+					if (vec2) {
+						*reinterpret_cast<uint2*>(p) = make_uint2(l2[0], l2[1]);
+					} else {
+						*reinterpret_cast<uint32_t*>(p) = l2[0];
+						if (xb + 4u < pitch2) *reinterpret_cast<uint32_t*>(p + 4) = l2[1];
+					}
+				}
+				if (need_finish) {
+					if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+					*reinterpret_cast<uint2*>(buf_a + ty * (ROW_BYTES / 4) + tx * 8) = make_uint2(l2[0], l2[1]);
+				}
+			} else {
+				// a thread holds one level-1 texel per row, its x neighbour lives in lane ^ 1; even lanes produce the level-2 texel
+				uint32_t own[2][4], nb[2][4];
+#pragma unroll
+				for (int j = 0; j < 2; ++j)
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						own[j][i] = l1[j][i];
+						nb[j][i] = __shfl_xor_sync(0xFFFFFFFFu, l1[j][i], 1);
+					}
+				if (!(lane & 1u)) {
+					const uint32_t sx2 = wt_swap(ex2[0]);
+					uint32_t ra[8], rb[8], l2[4];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						// row roles first (A row = level-1 row sy2), then texel roles (A texel = the pair's texel sx2)
+						const uint32_t a_own = sy2 ? own[1][i] : own[0][i], a_nb = sy2 ? nb[1][i] : nb[0][i];
+						const uint32_t b_own = sy2 ? own[0][i] : own[1][i], b_nb = sy2 ? nb[0][i] : nb[1][i];
+						ra[i] = sx2 ? a_nb : a_own; ra[4 + i] = sx2 ? a_own : a_nb;
+						rb[i] = sx2 ? b_nb : b_own; rb[4 + i] = sx2 ? b_own : b_nb;
+					}
+					const float tx2[1] = { wt_weight(ex2[0]) };
+					reduce_rows_2d_t<EK, CH, 8>(ra, rb, tx2, ty2, l2, P.no_double);
+					const uint32_t xb = tc.x * (ROW_BYTES / 4) + (tx >> 1) * 16u;
+					if (tc.y * (TL::TY / 4) + ty < H2 && xb < pitch2)
+						*reinterpret_cast<uint4*>(g2 + (uint64_t)ty * pitch2 + (tx >> 1) * 16u) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+					if (need_finish) {
+						if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+						*reinterpret_cast<uint4*>(buf_a + ty * (ROW_BYTES / 4) + (tx >> 1) * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+					}
+				}
+			}
+		}
+
+		// this warp's part of buf_a is written: hand the slot to the finisher pool (arrive = release)
+		if (need_finish) {
+			if (tid == 0) {
+				slot_tile[slot] = t; // only after this thread's wait on slot_empty above
+				slot_pos[slot] = tc;
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_full[slot]);
+		}
+		if (++s == stages) { s = 0; ++use; }
+		if (++slot == FLMIP_FINISHER_WARPS) { slot = 0; ++slot_use; }
+	}
+	if (need_finish) {
+		for (uint32_t k = 0; k < FLMIP_FINISHER_WARPS; ++k) {
+			if (slot_use > 0) mbar_wait(&slot_empty[slot], (slot_use - 1u) & 1u);
+			if (tid == 0) slot_tile[slot] = FLMIP_NO_TILE;
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&slot_full[slot]);
+			if (++slot == FLMIP_FINISHER_WARPS) { slot = 0; ++slot_use; }
+		}
+	}
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 	x += 0x9E3779B97F4A7C15ull;
 	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -1593,6 +2279,29 @@ FLMIP_FAST_KERNELS_FOR_KIND(8)
 FLMIP_FAST_KERNELS_FOR_KIND(9)
 FLMIP_FAST_KERNELS_FOR_KIND(10)
 FLMIP_FAST_KERNELS_FOR_KIND(11)
+#endif
+
+#define FLMIP_PTILE_KERNEL(K, CHN)                                                                                                  \
+	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_ptile2d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,     \
+																							   const __grid_constant__ flmip_ptile_params P) { \
+		ptile_body<K, CHN>(tmap, P);                                                                                                \
+	}
+#define FLMIP_PTILE_KERNELS_FOR_KIND(K) FLMIP_PTILE_KERNEL(K, 1) FLMIP_PTILE_KERNEL(K, 2) FLMIP_PTILE_KERNEL(K, 4)
+#ifdef FLMIP_DEV_ONLY
+FLMIP_PTILE_KERNEL(2, 4) FLMIP_PTILE_KERNEL(1, 4) FLMIP_PTILE_KERNEL(0, 4) FLMIP_PTILE_KERNEL(2, 1) FLMIP_PTILE_KERNEL(10, 2)
+#else
+FLMIP_PTILE_KERNELS_FOR_KIND(0)
+FLMIP_PTILE_KERNELS_FOR_KIND(1)
+FLMIP_PTILE_KERNELS_FOR_KIND(2)
+FLMIP_PTILE_KERNELS_FOR_KIND(3)
+FLMIP_PTILE_KERNELS_FOR_KIND(4)
+FLMIP_PTILE_KERNELS_FOR_KIND(5)
+FLMIP_PTILE_KERNELS_FOR_KIND(6)
+FLMIP_PTILE_KERNELS_FOR_KIND(7)
+FLMIP_PTILE_KERNELS_FOR_KIND(8)
+FLMIP_PTILE_KERNELS_FOR_KIND(9)
+FLMIP_PTILE_KERNELS_FOR_KIND(10)
+FLMIP_PTILE_KERNELS_FOR_KIND(11)
 #endif
 
 // 2D, texels below 16 bytes: 4 CTAs per SM (64 registers, no spills).  Measured on N2 (RGBA16F) with the per-CTA sampler table:

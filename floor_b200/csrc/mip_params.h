@@ -85,6 +85,36 @@ struct flmip_tile_params {
 	uint32_t block_sync; // 1: some produced level >= 2 contains a texel-2 fetch (block barriers instead of warp barriers)
 };
 
+// persistent TMA tile kernel, 2D images of any size whose source rows are 16-byte multiples (flmip_ptile2d_*): the single-pass
+// structure of flmip_fast2d_* (TMA ring, warp-specialised CTA, finisher pool, last tile of a layer finishes the chain) with the
+// general sampler weights of the reference, read from a per-image table instead of being 0.5.
+// Sampler table: one uint32 per destination texel coordinate, level and axis = the fp32 weight t of the "active" texel B
+// (0 < t <= 1, so bits 31 and 30 are free): bit 31 = roles swapped (A = 2g + 1, B = 2g instead of A = 2g, B = 2g + 1),
+// bit 30 = the texel-2 fetch of the reference (g = 0: A = 2, B = 0); see axis_fetch() in mip_kernels.cu.
+#ifndef FLMIP_PTILE_PATCH_BYTES
+#define FLMIP_PTILE_PATCH_BYTES 16384u // the level the tiles end on, of one layer, must fit here for the chain to finish in one launch
+#endif
+#ifndef FLMIP_PTILE_TAIL_TAB
+#define FLMIP_PTILE_TAIL_TAB 1024u      // sampler entries (x + y) of one level the last-tile stage keeps in shared memory
+#endif
+#define FLMIP_WTAB_SWAP 0x80000000u
+#define FLMIP_WTAB_TEXEL2 0x40000000u
+struct flmip_ptile_params {
+	uint64_t base;
+	uint64_t level_off[FLMIP_MAX_LEVELS]; // byte offset of every level of the image (absolute level numbers)
+	uint64_t wtab;                        // device address of the sampler table
+	uint64_t counters;                    // uint32[layers]: tiles of the layer that have finished their tile stage
+	uint64_t sched;                       // uint32[2]: dynamic tile scheduler (as in flmip_fast_params)
+	uint32_t wtab_off[FLMIP_MAX_LEVELS][2]; // first entry of (destination level, axis) in the table
+	uint32_t dim[FLMIP_MAX_LEVELS][2];    // texels of every level
+	uint32_t src_level;                   // the level the tensor map covers (0, or where a previous launch stopped)
+	uint32_t tile_last;                   // last level the tiles produce on their own (<= src_level + 6)
+	uint32_t last_level;                  // last level of this launch (> tile_last: the last tile of a layer carries on)
+	uint32_t tiles[2], layers, total_tiles, stages, no_double;
+	uint32_t unit_shift;                  // log2(tiles per unit): 2 when every CTA has many tiles (one publish per 4 tiles), else 0
+	uint32_t vec1, vec2;                  // rows of level src + 1 / src + 2 start on 16- / 8-byte (16-byte texels: 16-byte) boundaries: full-width vector stores
+};
+
 struct flmip_fill_params {
 	uint64_t dst;             // device address of level 0 of the first layer to fill
 	uint64_t elems_per_layer; // texels * channels

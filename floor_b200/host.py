@@ -149,10 +149,10 @@ class device_queue:
 class device_image:
     def __init__(self, cqueue: device_queue, image_dim, image_type: int, data=None,
                  flags: int = MEMORY_FLAG.HOST_READ_WRITE, mip_level_limit: int = 0, no_double: bool = False,
-                 force_generic: bool = False, units: bool | None = None, force_tiled: bool = False):
-        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED, LevelInfo
+                 force_generic: bool = False, units: bool | None = None, force_tiled: bool = False, no_tma_tiles: bool = False, tma_tiles: str | None = None):
+        from . import IMAGE_NO_DOUBLE, IMAGE_FORCE_GENERIC, IMAGE_UNITS_ALWAYS, IMAGE_UNITS_NEVER, IMAGE_FORCE_TILED, IMAGE_NO_TMA_TILES, LevelInfo
         self.dev = cqueue.dev
-        self._create_kw = {"no_double": no_double, "force_generic": force_generic, "units": units, "force_tiled": force_tiled}
+        self._create_kw = {"no_double": no_double, "force_generic": force_generic, "units": units, "force_tiled": force_tiled, "no_tma_tiles": no_tma_tiles, "tma_tiles": tma_tiles}
         dim = list(image_dim) + [0] * (4 - len(image_dim))
         # device_image::handle_image_type (device_image.hpp:70-91)
         if flags & MEMORY_FLAG.GENERATE_MIP_MAPS:
@@ -162,6 +162,10 @@ class device_image:
         cflags = (IMAGE_NO_DOUBLE if no_double else 0) | (IMAGE_FORCE_GENERIC if force_generic else 0)
         cflags |= 0 if units is None else (IMAGE_UNITS_ALWAYS if units else IMAGE_UNITS_NEVER)
         cflags |= IMAGE_FORCE_TILED if force_tiled else 0
+        cflags |= IMAGE_NO_TMA_TILES if no_tma_tiles else 0
+        # tuning: "always" (whatever the tile count), "+split" / "+nosplit" (two levels per launch: always / never)
+        if tma_tiles:
+            cflags |= (64 if "always" in tma_tiles else 0) | (128 if "+split" in tma_tiles else 0) | (256 if "+nosplit" in tma_tiles else 0)
         _check(_L().flmip_image_create(self.dev.index, image_type, _u32x(dim, 4), mip_level_limit, cflags,
                                        ctypes.byref(self._handle)))
         n = ctypes.c_uint32()
@@ -213,7 +217,9 @@ class device_image:
     def plan(self):
         a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         _check(_L().flmip_image_plan(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return {"single_pass": bool(a.value), "fast_levels": b.value, "launches": c.value}
+        d = ctypes.c_uint32()
+        _check(_L().flmip_image_plan_tma_tile_launches(self._handle, ctypes.byref(d)))
+        return {"single_pass": bool(a.value), "fast_levels": b.value, "launches": c.value, "tma_tile_launches": d.value}
 
     # ---- THE hot path ----
     def generate_mip_map_chain(self, cqueue: device_queue):

@@ -33,6 +33,10 @@ extern "C" {
 #define FLMIP_IMAGE_FORCE_GENERIC 2u /* only the literal one-launch-per-level kernel (validation / A-B timing) */
 #define FLMIP_IMAGE_UNITS_ALWAYS 4u  /* single-pass kernel: schedule 2x2(x2)-tile units whenever the tile grid allows it */
 #define FLMIP_IMAGE_UNITS_NEVER 8u   /* single-pass kernel: always schedule single tiles (default: by image size) */
+#define FLMIP_IMAGE_NO_TMA_TILES 32u /* tile kernel: never the persistent TMA form (flmip_ptile2d_*), always the LDG form (validation / A-B timing) */
+#define FLMIP_IMAGE_TMA_TILES_ALWAYS 64u   /* tuning: the persistent TMA tile kernel wherever a level qualifies, however few tiles it has */
+#define FLMIP_IMAGE_TMA_TILES_SPLIT 128u    /* tuning: always stream two levels per launch of it (default: by tiles per resident CTA) */
+#define FLMIP_IMAGE_TMA_TILES_NO_SPLIT 256u /* tuning: never */
 #define FLMIP_IMAGE_FORCE_TILED 16u  /* never use the persistent single-pass kernel: multi-level tile kernel for every level (validation / A-B timing) */
 
 typedef struct flmip_image_s* flmip_image;
@@ -113,6 +117,13 @@ int flmip_image_get_level_info(flmip_image img, uint32_t level, flmip_level_info
 int flmip_image_device_ptr(flmip_image img, uint64_t* out);         /* CUdeviceptr of level 0 */
 /* 1 if generate uses the single-pass kernel; *fast_levels = number of levels (incl. level 0) it covers */
 int flmip_image_plan(flmip_image img, uint32_t* uses_single_pass, uint32_t* fast_levels, uint32_t* launches);
+/* one entry of the sampler table the persistent tile kernel reads (host arithmetic only, no GPU needed): the reference's linear
+ * fetch for destination texel g along an axis whose source level has n texels (mip_map_minify.hpp:106, host_image.hpp:141-174,
+ * 869-894): fp32 bits of the weight t of the active texel B; bit 31: A = 2g + 1, B = 2g (else A = 2g, B = 2g + 1); bit 30: the
+ * texel-2 fetch (g = 0: A = 2, B = 0) */
+int flmip_sampler_table_entry(uint32_t g, uint32_t n, uint32_t* out);
+/* number of those launches that are the persistent TMA tile kernel (flmip_ptile2d_*) */
+int flmip_image_plan_tma_tile_launches(flmip_image img, uint32_t* out);
 
 /* -- host <-> device: cuda_image::write / map / unmap copies (cuda_image.cpp:588-813).
  *    Whole levels [level_first, level_last] (inclusive, like mip_level_range) in host layout; async on `stream`. */

@@ -216,3 +216,96 @@ def test_fastest_gpu_and_device_clock(gpu_ctx):
     assert dev.clock > 500 and dev.mem_bus_width >= 1024 and dev.l2_cache_size > (32 << 20)
     best = ctx.get_device("FASTEST_GPU")
     assert all(d.units * d.clock <= best.units * best.clock for d in ctx.get_devices())
+
+
+ALL_FORMATS = [T.R8, T.RG8, T.RGBA8, T.R16, T.RG16, T.RGBA16, T.R8I_NORM, T.RG8I_NORM, T.RGBA8I_NORM, T.R16I_NORM, T.RG16I_NORM,
+               T.RGBA16I_NORM, T.R8UI, T.RG8UI, T.RGBA8UI, T.R8I, T.RG8I, T.RGBA8I, T.R16UI, T.RG16UI, T.RGBA16UI, T.R16I, T.RG16I,
+               T.RGBA16I, T.R32UI, T.RG32UI, T.RGBA32UI, T.R32I, T.RG32I, T.RGBA32I, T.R16F, T.RG16F, T.RGBA16F, T.R32F, T.RG32F,
+               T.RGBA32F]
+
+
+def texel2_size(n: int) -> bool:
+    """sizes N with fl(fl(1/N) * N) == pred(1.0f): destination texel 0 reads source texels 0 and 2 (tests/test_npot_weights.py)"""
+    f = np.float32
+    return n >= 3 and f(f(1.0) / f(n)) * f(n) == np.nextafter(f(1.0), f(0.0))
+
+
+def chain(gpu_ctx, l0, dim, t, **kw):
+    ctx, dev, q = gpu_ctx
+    img = ctx.create_image(q, dim, t, **kw)
+    img.upload_levels(q, l0, 0, 0)
+    img.generate_mip_map_chain(q)
+    out = img.download_levels(q)
+    plan = img.plan()
+    img.destroy()
+    return out, plan
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_persistent_tma_tile_kernel_all_formats(gpu_ctx, oracle_mod, fmt):
+    """flmip_ptile2d_*: NPOT 2D images whose rows are 16-byte multiples -- partial border tiles in x and y, odd level sizes, role
+    swaps and weights != 0.5 (1080, 1000, 600 ...), layers, and the texel-2 fetch of the reference deep in the chain (2624 = 41 << 6,
+    1312 = 41 << 5: inside the tile stage for narrow texels, cut short for wide ones).  Both forms: two levels per launch (the
+    default for large images; the planner's size thresholds are lifted here) and the one-launch form, where the finisher pool
+    reduces every tile further and the last tile of a layer finishes the chain."""
+    bpp = it.bytes_per_pixel(fmt)
+    w16 = 16 // bpp if bpp < 16 else 1  # texels per 16 bytes
+    def wd(w):  # a width near w whose row is a 16-byte multiple and at least one tile row
+        return max(-(-w // w16) * w16, 512 // bpp)
+    cases = [(T.IMAGE_2D, (wd(1080), 600)), (T.IMAGE_2D, (wd(1000), 70)), (T.IMAGE_2D_ARRAY, (wd(600), 333, 3)), (T.IMAGE_2D, (wd(2624), 188)),
+             (T.IMAGE_2D, (wd(1312), 200)), (T.IMAGE_CUBE, (wd(720), wd(720))), (T.IMAGE_2D, (wd(517), 64)), (T.IMAGE_2D, (wd(96), 1504))]
+    for base, dim in cases:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 900 + (fmt & 0xFFFF))
+        want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8)
+        for mode in ("always+nosplit", "always"):
+            got, plan = chain(gpu_ctx, l0, dim, t, tma_tiles=mode)
+            # (a level whose first or second destination level takes the reference's texel-2 fetch -- 2624 = 41 << 6, 1312 = 41 << 5,
+            #  166 = 83 << 1 ... -- is never a TMA source: levels 1 and 2 are produced in registers; the LDG kernel serves it)
+            assert not plan["single_pass"] and (plan["tma_tile_launches"] >= 1 or any(texel2_size(d >> k) for d in dim[:2] for k in (0, 1))), (dim, mode, plan)
+            if not np.array_equal(got, want):
+                bad = np.nonzero(got != want)[0]
+                raise AssertionError(f"ptile {mode} {hex(t)} {dim} plan {plan}: {bad.size} differing bytes, first at {int(bad[0])}")
+        got2, plan2 = chain(gpu_ctx, l0, dim, t, no_tma_tiles=True)
+        assert plan2["tma_tile_launches"] == 0 and np.array_equal(got2, want), (dim, plan2)
+        if it.bits_per_channel(t) == 16 and (t & T.FLAG_NORMALIZED):
+            got, _ = chain(gpu_ctx, l0, dim, t, no_double=True, tma_tiles="always+nosplit")
+            assert np.array_equal(got, oracle_mod.generate_mip_map_chain(l0, dim, t, no_double=True, threads=8)), (dim, "no_double")
+
+
+def test_persistent_tma_tile_kernel_plans(gpu_ctx, oracle_mod):
+    """which launches the planner picks.  Default: the TMA kernel streams two levels of a level with a long queue of tiles per resident
+    CTA (threshold by texel size, never for 16-byte texels), everything else is the LDG kernel's; one-launch form on request: the
+    whole chain where the post-tile level of a layer fits the patch (N1, N2 of bench.py), two launches for a larger image; never
+    for rows that are no 16-byte multiple / texel-2 sizes at levels 1-2 / images smaller than a tile / volumes"""
+    ctx, dev, q = gpu_ctx
+    big = 12 * 2 * dev.units  # tiles that make an RGBA8 level qualify by default
+    layers = -(-big // (8 * 10))  # 1000 x 600 RGBA8: 8 x 10 tiles per layer
+    for base, fmt, dim, kw, launches, tma in [
+            (T.IMAGE_2D, T.RGBA8, (3840, 2160), {}, 2, 0), (T.IMAGE_2D_ARRAY, T.RGBA16F, (1920, 1080, 4), {}, 2, 0),
+            (T.IMAGE_2D_ARRAY, T.RGBA8, (1000, 600, layers), {}, 3, 1), (T.IMAGE_2D, T.R8, (7680, 4320), {}, None, 1),
+            (T.IMAGE_2D, T.RGBA32F, (7680, 4320), {}, 2, 0),
+            (T.IMAGE_2D, T.RGBA8, (3840, 2160), {"tma_tiles": "always+nosplit"}, 1, 1), (T.IMAGE_2D_ARRAY, T.RGBA16F, (1920, 1080, 4), {"tma_tiles": "always+nosplit"}, 1, 1),
+            (T.IMAGE_2D, T.RGBA8, (8000, 6000), {"tma_tiles": "always+nosplit"}, 2, 1), (T.IMAGE_2D, T.RGBA8, (1002, 600), {"tma_tiles": "always"}, 2, 0),
+            (T.IMAGE_2D, T.RGBA8, (164, 1000), {"tma_tiles": "always"}, 2, 0), (T.IMAGE_2D, T.RGBA8, (100, 60), {"tma_tiles": "always"}, 1, 0),
+            (T.IMAGE_3D, T.R32F, (300, 200, 100), {"tma_tiles": "always"}, 2, 0), (T.IMAGE_2D, T.RGBA32F, (1001, 999), {"tma_tiles": "always+nosplit"}, 1, 1)]:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 78)
+        got, plan = chain(gpu_ctx, l0, dim, t, **kw)
+        assert plan["tma_tile_launches"] == tma and (launches is None or plan["launches"] == launches), (dim, kw, plan)
+        assert np.array_equal(got, oracle_mod.generate_mip_map_chain(l0, dim, t, threads=16)), (dim, kw)
+    # regeneration from a dirty level goes through the same planner
+    dim, t = (3840, 2160), T.IMAGE_2D | T.RGBA8 | M
+    img = ctx.create_image(q, dim, t, tma_tiles="always+nosplit")
+    l0 = oracle_mod.fill_synthetic(dim, t, 79)
+    img.upload_levels(q, l0, 0, 0)
+    img.generate_mip_map_chain(q)
+    full = img.download_levels(q)
+    lvl2 = oracle_mod.fill_synthetic((960, 540), t, 80)
+    img.upload_levels(q, lvl2, 2, 2)
+    img.enqueue_mip_map_chain(q, 2)
+    got = img.download_levels(q)
+    o2 = img.levels[2]["offset"]
+    want_tail = oracle_mod.generate_mip_map_chain(lvl2, (960, 540), t, threads=16)
+    assert np.array_equal(got[:o2], full[:o2]) and np.array_equal(got[o2:], want_tail)
+    img.destroy()

@@ -70,3 +70,27 @@ def test_host_planner_knows_the_quirk_sizes(built_lib):
     n = np.arange(3, 200, dtype=np.int64)
     q = set(int(x) for x in n[quirk_sizes(n)])
     assert {41, 47, 55, 61, 82, 83, 94, 97} <= q and 64 not in q and 100 not in q
+
+
+def test_host_sampler_table_matches_the_float32_emulation(built_lib):
+    """the persistent TMA tile kernel (flmip_ptile2d_*) reads roles and weights from a table flmip.cpp computes on the host:
+    every entry must be the float32 computation above, bit for bit (weight), with the right role / texel-2 flags"""
+    import ctypes
+    rng = np.random.default_rng(11)
+    sizes = np.unique(np.concatenate([np.arange(2, 300), rng.integers(300, 1 << 15, 120), np.array([1080, 1920, 2160, 3840, 7680, 4095, 4097, 32767, 32768])]))
+    e = ctypes.c_uint32()
+    for n in sizes:
+        g = np.arange(int(n) >> 1, dtype=np.int64)
+        a, b, w = fetch_pair(np.full_like(g, n), g)
+        wbits = w.view(np.uint32)
+        for gi in (g if n < 300 else np.unique(np.concatenate([g[:3], g[-3:], rng.choice(g, 40)]))):
+            assert built_lib.flmip_sampler_table_entry(int(gi), int(n), ctypes.byref(e)) == 0, (n, gi)
+            v = e.value
+            assert (v & 0x3FFFFFFF) == int(wbits[gi]), (n, gi, hex(v), hex(int(wbits[gi])))
+            if a[gi] == 2 and b[gi] == 0 and gi == 0:
+                assert v >> 30 == 1, (n, gi)
+            elif a[gi] == 2 * gi + 1:
+                assert v >> 30 == 2 and b[gi] == 2 * gi, (n, gi)
+            else:
+                assert v >> 30 == 0 and a[gi] == 2 * gi and b[gi] == 2 * gi + 1, (n, gi)
+    assert built_lib.flmip_sampler_table_entry(5, 10, ctypes.byref(e)) != 0  # g outside the destination level
