@@ -305,7 +305,7 @@ constexpr uint64_t T_FORMAT_MASK = 0x3Full, T_COMPRESSION_MASK = 0x3C0ull, T_DAT
 constexpr uint64_t T_INT = 0x1000ull, T_UINT = 0x2000ull, T_FLOAT = 0x3000ull;
 constexpr uint64_t T_FLAG_ARRAY = 1ull << 20, T_FLAG_MSAA = 1ull << 22, T_FLAG_CUBE = 1ull << 23, T_FLAG_DEPTH = 1ull << 24,
 				   T_FLAG_STENCIL = 1ull << 25, T_FLAG_MIPMAPPED = 1ull << 27, T_FLAG_NORMALIZED = 1ull << 30;
-constexpr uint32_t FMT_8 = 11, FMT_16 = 18, FMT_32 = 22;
+constexpr uint32_t FMT_2 = 2, FMT_4 = 4, FMT_8 = 11, FMT_16 = 18, FMT_32 = 22;
 
 bool is_pot(uint32_t v) { return v != 0 && (v & (v - 1)) == 0; }
 
@@ -370,16 +370,28 @@ int decode_type(flmip_image_s& im) {
 	im.dc = (uint32_t)((t >> 16) & 3u);
 	im.channels = (uint32_t)((t >> 14) & 3u) + 1u;
 	const uint32_t fmt = (uint32_t)(t & T_FORMAT_MASK);
-	im.bpc = fmt == FMT_8 ? 8 : fmt == FMT_16 ? 16 : fmt == FMT_32 ? 32 : 0;
+	im.bpc = fmt == FMT_2 ? 2 : fmt == FMT_4 ? 4 : fmt == FMT_8 ? 8 : fmt == FMT_16 ? 16 : fmt == FMT_32 ? 32 : 0;
 	if (im.dc < 1 || im.dc > 3) return fail(FLMIP_ERR_INVALID, "invalid image dimensionality in type %#llx", (unsigned long long)t);
 	if (t & T_COMPRESSION_MASK) return fail(FLMIP_ERR_UNSUPPORTED, "compressed images cannot be minified (device_image.hpp:519-525)");
 	if (t & T_FLAG_MSAA) return fail(FLMIP_ERR_UNSUPPORTED, "msaa is not supported (mip_map_minify.hpp:95)");
 	if (t & T_FLAG_STENCIL) return fail(FLMIP_ERR_UNSUPPORTED, "stencil images have no minification kernel");
-	if (im.bpc == 0) return fail(FLMIP_ERR_UNSUPPORTED, "unsupported image format %u (8/16/32 bit per channel only)", fmt);
-	if (im.channels == 3) return fail(FLMIP_ERR_UNSUPPORTED, "3-channel images are unsupported with CUDA (cuda_image.cpp:173-180)");
+	if (im.bpc == 0) return fail(FLMIP_ERR_UNSUPPORTED, "unsupported image format %u (2/4/8/16/32 bit per channel only)", fmt);
+	// 3-channel images: the reference's CUDA backend rejects them because a CUarray cannot hold them (cuda_image.cpp:173-180); its
+	// Host-Compute backend minifies them, and so does this path: linear memory has no such restriction (literal kernel).
 	if (im.dc == 3 && (t & (T_FLAG_ARRAY | T_FLAG_CUBE))) return fail(FLMIP_ERR_UNSUPPORTED, "3D array images have no minification kernel");
 	const uint64_t dt = t & T_DATA_TYPE_MASK;
 	const bool norm = (t & T_FLAG_NORMALIZED) != 0;
+	if (im.bpc < 8) {
+		// FORMAT_2 / FORMAT_4 (host_image.hpp:341-353, 419-446, dispatched at :1167-1186): normalized only, and only where a texel is
+		// a whole number of bytes -- the reference sizes images by bits (image_types.hpp:675-691) but addresses texels by
+		// ceil(bits / 8) bytes (host_image.hpp:235-271), so R2 / RG2 / RGB2 / R4 / RGB4 images are smaller than what its own kernels touch
+		if (!norm || (dt != T_UINT && dt != T_INT)) return fail(FLMIP_ERR_UNSUPPORTED, "2 / 4-bit formats only exist as normalized integers");
+		if ((im.bpc * im.channels) % 8u) return fail(FLMIP_ERR_UNSUPPORTED, "%u x %u-bit texels are no whole number of bytes (the reference's own size helpers and kernels disagree on such images)", im.channels, im.bpc);
+		if (t & T_FLAG_DEPTH) return fail(FLMIP_ERR_UNSUPPORTED, "only D32F depth images can be minified");
+		im.elem_kind = im.bpc == 4 ? (dt == T_INT ? FLMIP_EK_SNORM4 : FLMIP_EK_UNORM4) : (dt == T_INT ? FLMIP_EK_SNORM2 : FLMIP_EK_UNORM2);
+		im.bpp = im.bpc * im.channels / 8u;
+		return FLMIP_OK;
+	}
 	if (dt == T_FLOAT) {
 		if (im.bpc == 32) im.elem_kind = FLMIP_EK_F32;
 		else if (im.bpc == 16) im.elem_kind = FLMIP_EK_F16;
@@ -430,6 +442,7 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	im.fast = false;
 	if (flags & FLMIP_IMAGE_FORCE_GENERIC) return FLMIP_OK;
 	if (im.level_count < 2 || im.dc < 2) return FLMIP_OK;
+	if (im.channels == 3 || im.elem_kind >= FLMIP_EK_COUNT) return FLMIP_OK; // literal kernel only
 	const bool is3d = im.dc == 3;
 	const uint32_t W = im.dim[0], H = im.dim[1], D = is3d ? im.dim[2] : 1u;
 	if (!is_pot(W) || !is_pot(H) || !is_pot(D)) return FLMIP_OK;
@@ -1052,7 +1065,8 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 		im->fast = false;
 		rc = FLMIP_OK;
 	}
-	if (rc == FLMIP_OK && im->dc >= 2 && ((flags & FLMIP_IMAGE_FORCE_TILED) || !(flags & FLMIP_IMAGE_FORCE_GENERIC))) {
+	const bool literal_only = im->channels == 3 || im->elem_kind >= FLMIP_EK_COUNT; // 3-channel and 2 / 4-bit formats
+	if (rc == FLMIP_OK && im->dc >= 2 && !literal_only && ((flags & FLMIP_IMAGE_FORCE_TILED) || !(flags & FLMIP_IMAGE_FORCE_GENERIC))) {
 		char name[64];
 		snprintf(name, sizeof(name), "flmip_tile%ud_k%u_c%u", im->dc, im->elem_kind, im->channels);
 		im->tile_name = name;
@@ -1413,6 +1427,7 @@ int flmip_image_create_tiled_twin(flmip_image img, void** out_mipmapped_array) {
 	if (check_image(img) || !out_mipmapped_array) return fail(FLMIP_ERR_INVALID, "null argument");
 	*out_mipmapped_array = nullptr;
 	if (img->dc < 2) return fail(FLMIP_ERR_UNSUPPORTED, "tiled interop covers 2D, 2D-array, cube, cube-array and 3D images");
+	if (img->channels == 3 || img->elem_kind >= FLMIP_EK_COUNT) return fail(FLMIP_ERR_UNSUPPORTED, "a CUarray holds 1, 2 or 4 channels of 8, 16 or 32 bits (cuda_image.cpp:173-248)");
 	// format LUT of cuda_image.cpp:197-207 (normalization is a property of the texture object, not of the array)
 	CUarray_format fmt;
 	switch (img->elem_kind) {
@@ -1634,7 +1649,7 @@ int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t lay
 	flmip_fill_params F;
 	memset(&F, 0, sizeof(F));
 	F.dst = img->mem;
-	F.elems_per_layer = img->levels[0].slice_size / (img->bpc / 8u);
+	F.elems_per_layer = img->levels[0].slice_size / (img->bpc >= 8u ? img->bpc / 8u : 1u); // 2 / 4-bit formats: one pattern element per storage byte
 	F.config_id = config_id;
 	F.layer_id0 = layer_id0;
 	F.layers = img->layers;

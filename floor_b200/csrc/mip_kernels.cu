@@ -935,7 +935,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		// Depth: a fetched unit is committed to this CTA, so every fetch in flight is work the last wave cannot rebalance.  A unit
 		// of 2 x 2 (x 2) tiles lasts longer than a round trip: 2 in flight (C2 +1.3 %, C5 +2.7 % over 4; 8 and 16 are slower
 		// still, profiles/r1/10_timeline.txt); single tiles need FLMIP_SCHED_PREFETCH.
-		const uint32_t PF = P.unit_shift ? 2u : FLMIP_SCHED_PREFETCH;
+		const uint32_t PF = P.unit_shift ? FLMIP_UNIT_PREFETCH : FLMIP_SCHED_PREFETCH;
 		uint32_t* const sched = reinterpret_cast<uint32_t*>(P.sched);
 		// The first unit of a CTA is its own index (no round trip before the first load); the counter hands out the rest.
 		uint32_t pf = FLMIP_NO_TILE;
@@ -1195,10 +1195,37 @@ __device__ __forceinline__ float wrap01(float v) { // const_math.hpp:859-869 wit
 	return fmodf(v, 1.0f);
 }
 
+// FORMAT_2 / FORMAT_4 normalized texels (host_image.hpp:333-383, 391-460): channel i sits at bits 6 - 2i of byte 0 (2 bits) or in
+// the high (even i) / low nibble of byte i / 2 (4 bits).  The signed variants reproduce the reference as written: its sign fix-up
+// `x & high_bit != 0u` parses as `x & 1`, so a channel with bit 0 set becomes -(x ^ high_bit) (pinned against the reference's
+// own build: tests/test_reference_pin.py).
+template <int BITS, bool SIGNED> __device__ __forceinline__ float packed_dec(const uint8_t* p, uint32_t i) {
+	const uint32_t v = BITS == 2 ? (p[0] >> (6u - 2u * i)) & 0x3u : (p[i >> 1] >> ((i & 1u) ? 0u : 4u)) & 0xFu;
+	if constexpr (!SIGNED) {
+		return __fmul_rn(__uint2float_rn(v), BITS == 2 ? (float)(1.0 / 3.0) : (float)(1.0 / 15.0));
+	} else {
+		int sv = (int)v;
+		if (v & 1u) sv = -(int)(signed char)(v ^ (1u << (BITS - 1)));
+		return __fmul_rn(__int2float_rn(sv), BITS == 2 ? 1.0f : (float)(1.0 / 7.0));
+	}
+}
+template <int BITS, bool SIGNED> __device__ __forceinline__ uint32_t packed_enc(float c) {
+	if constexpr (!SIGNED) {
+		const uint32_t q = (uint32_t)(unsigned char)__float2int_rz(__fmul_rn(c, (float)((1 << BITS) - 1)));
+		return q & ((1u << BITS) - 1u);
+	} else {
+		const int q = (int)(signed char)__float2int_rz(__fmul_rn(c, (float)((1 << (BITS - 1)) - 1)));
+		return ((uint32_t)q & ((1u << (BITS - 1)) - 1u)) | (q < 0 ? 1u << (BITS - 1) : 0u);
+	}
+}
+
 template <uint32_t EK>
 __device__ __forceinline__ void generic_texel(const flmip_generic_params& P, uint64_t idx) {
-	using C = Codec<EK>;
-	const uint32_t dc = P.dc, ch = P.channels, bpp = C::BYTES * ch;
+	constexpr bool PACKED = EK >= FLMIP_EK_COUNT;
+	constexpr int PBITS = (EK == FLMIP_EK_UNORM2 || EK == FLMIP_EK_SNORM2) ? 2 : 4;
+	constexpr bool PSIGNED = (EK == FLMIP_EK_SNORM4 || EK == FLMIP_EK_SNORM2);
+	using C = Codec<PACKED ? (uint32_t)FLMIP_EK_UNORM8 : EK>; // packed formats sample as float: only lerp_t is used from the codec
+	const uint32_t dc = P.dc, ch = P.channels, bpp = PACKED ? (PBITS * ch) >> 3 : C::BYTES * ch;
 	// idx -> (x, y, z, layer)
 	uint32_t g[3] = { 0, 0, 0 };
 	uint64_t rem = idx;
@@ -1237,11 +1264,15 @@ __device__ __forceinline__ void generic_texel(const flmip_generic_params& P, uin
 		const uint32_t texel = (dc == 1 ? c[0] : (dc == 2 ? P.src_dim[0] * c[1] + c[0] : P.src_dim[0] * P.src_dim[1] * c[2] + P.src_dim[0] * c[1] + c[0]));
 		const uint8_t* p = src + (uint64_t)texel * bpp;
 		for (uint32_t i = 0; i < ch; ++i) {
-			uint32_t raw;
-			if constexpr (C::BYTES == 4) raw = *reinterpret_cast<const uint32_t*>(p + 4 * i);
-			else if constexpr (C::BYTES == 2) raw = *reinterpret_cast<const unsigned short*>(p + 2 * i);
-			else raw = p[i];
-			v[k][i] = C::dec(raw);
+			if constexpr (PACKED) {
+				v[k][i] = __float_as_uint(packed_dec<PBITS, PSIGNED>(p, i));
+			} else {
+				uint32_t raw;
+				if constexpr (C::BYTES == 4) raw = *reinterpret_cast<const uint32_t*>(p + 4 * i);
+				else if constexpr (C::BYTES == 2) raw = *reinterpret_cast<const unsigned short*>(p + 2 * i);
+				else raw = p[i];
+				v[k][i] = C::dec(raw);
+			}
 		}
 	}
 	for (uint32_t d = 0; d < dc; ++d) {
@@ -1251,6 +1282,16 @@ __device__ __forceinline__ void generic_texel(const flmip_generic_params& P, uin
 	}
 	const uint32_t texel = (dc == 1 ? g[0] : (dc == 2 ? P.dst_dim[0] * g[1] + g[0] : P.dst_dim[0] * P.dst_dim[1] * g[2] + P.dst_dim[0] * g[1] + g[0]));
 	uint8_t* q = reinterpret_cast<uint8_t*>(P.base) + P.dst_off + (uint64_t)layer * P.dst_slice + (uint64_t)texel * bpp;
+	if constexpr (PACKED) {
+		uint32_t bytes[2] = { 0u, 0u }; // the texel's bytes are rebuilt from zero (insert_channels memsets them)
+		for (uint32_t i = 0; i < ch; ++i) {
+			const uint32_t bits = packed_enc<PBITS, PSIGNED>(__uint_as_float(v[0][i]));
+			if constexpr (PBITS == 2) bytes[0] |= bits << (6u - 2u * i);
+			else bytes[i >> 1] |= bits << ((i & 1u) ? 0u : 4u);
+		}
+		for (uint32_t b = 0; b < bpp; ++b) q[b] = (uint8_t)bytes[b];
+		return;
+	}
 	for (uint32_t i = 0; i < ch; ++i) {
 		const uint32_t raw = C::enc(v[0][i], P.no_double);
 		if constexpr (C::BYTES == 4) *reinterpret_cast<uint32_t*>(q + 4 * i) = raw;
@@ -2226,6 +2267,10 @@ extern "C" __global__ void __launch_bounds__(256) flmip_generic(const __grid_con
 		case FLMIP_EK_I16: generic_texel<FLMIP_EK_I16>(P, idx); break;
 		case FLMIP_EK_U32: generic_texel<FLMIP_EK_U32>(P, idx); break;
 		case FLMIP_EK_I32: generic_texel<FLMIP_EK_I32>(P, idx); break;
+		case FLMIP_EK_UNORM4: generic_texel<FLMIP_EK_UNORM4>(P, idx); break;
+		case FLMIP_EK_SNORM4: generic_texel<FLMIP_EK_SNORM4>(P, idx); break;
+		case FLMIP_EK_UNORM2: generic_texel<FLMIP_EK_UNORM2>(P, idx); break;
+		case FLMIP_EK_SNORM2: generic_texel<FLMIP_EK_SNORM2>(P, idx); break;
 		default: break;
 	}
 }

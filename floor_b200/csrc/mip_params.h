@@ -10,6 +10,9 @@
 #ifndef FLMIP_SCHED_PREFETCH
 #define FLMIP_SCHED_PREFETCH 4u   // tile-index fetches the producer keeps in flight
 #endif
+#ifndef FLMIP_UNIT_PREFETCH
+#define FLMIP_UNIT_PREFETCH 1u    // ... when the work items are units of 2 x 2 (x 2) tiles: a unit outlasts the round trip, and every prefetched unit is committed to its CTA (2 -> 1: C3 +0.7 %, C5 +0.1 %, C2 +-0, profiles/r2/06_unit_prefetch_ab.txt)
+#endif
 #define FLMIP_UNIT_PATCH_BYTES 512u    // remainders of the tiles of one unit: at most 8 x (1 x 2 x 2 texels of 16 bytes)
 #define FLMIP_NO_TILE 0xFFFFFFFFu // end-of-work sentinel in the tile ring / cascade slots
 #define FLMIP_BLOCK_THREADS ((8 + 1 + FLMIP_FINISHER_WARPS) * 32)
@@ -29,7 +32,13 @@ enum flmip_elem_kind : uint32_t {
 	FLMIP_EK_I16,
 	FLMIP_EK_U32,
 	FLMIP_EK_I32,
-	FLMIP_EK_COUNT
+	FLMIP_EK_COUNT, // kinds the single-pass / tile kernels are instantiated for
+	// FORMAT_2 / FORMAT_4 normalized formats (host_image.hpp:341-353, 419-446): 2 / 4 bits per channel packed into whole bytes
+	// (RGBA2: 1 byte, RG4: 1 byte, RGBA4: 2 bytes); served by the literal kernel (flmip_generic) only
+	FLMIP_EK_UNORM4 = FLMIP_EK_COUNT,
+	FLMIP_EK_SNORM4,
+	FLMIP_EK_UNORM2,
+	FLMIP_EK_SNORM2
 };
 
 // one destination level, any size (NPOT capable): the general path

@@ -94,6 +94,20 @@ class IMAGE_TYPE:
     RGB16F = CHANNELS_3 | FORMAT_16 | FLOAT
     RGB32F = CHANNELS_3 | FORMAT_32 | FLOAT
     D32F = IMAGE_DEPTH | FORMAT_32 | FLOAT
+    # 3-channel formats (Host-Compute minifies them; the reference's CUDA backend cannot store them: cuda_image.cpp:173-180)
+    RGB16 = CHANNELS_3 | FORMAT_16 | UINT | FLAG_NORMALIZED
+    RGB8I_NORM = CHANNELS_3 | FORMAT_8 | INT | FLAG_NORMALIZED
+    RGB16I_NORM = CHANNELS_3 | FORMAT_16 | INT | FLAG_NORMALIZED
+    RGB8UI, RGB8I = CHANNELS_3 | FORMAT_8 | UINT, CHANNELS_3 | FORMAT_8 | INT
+    RGB16UI, RGB16I = CHANNELS_3 | FORMAT_16 | UINT, CHANNELS_3 | FORMAT_16 | INT
+    RGB32UI, RGB32I = CHANNELS_3 | FORMAT_32 | UINT, CHANNELS_3 | FORMAT_32 | INT
+    # FORMAT_2 / FORMAT_4 normalized formats whose texel is a whole number of bytes (host_image.hpp:341-353, 1167-1186)
+    RGBA2 = CHANNELS_4 | FORMAT_2 | UINT | FLAG_NORMALIZED
+    RGBA2I_NORM = CHANNELS_4 | FORMAT_2 | INT | FLAG_NORMALIZED
+    RG4 = CHANNELS_2 | FORMAT_4 | UINT | FLAG_NORMALIZED
+    RG4I_NORM = CHANNELS_2 | FORMAT_4 | INT | FLAG_NORMALIZED
+    RGBA4 = CHANNELS_4 | FORMAT_4 | UINT | FLAG_NORMALIZED
+    RGBA4I_NORM = CHANNELS_4 | FORMAT_4 | INT | FLAG_NORMALIZED
 
 
 class MEMORY_FLAG:
@@ -115,7 +129,7 @@ def channel_count(t: int) -> int:
 
 
 def bits_per_channel(t: int) -> int:
-    return {IMAGE_TYPE.FORMAT_8: 8, IMAGE_TYPE.FORMAT_16: 16, IMAGE_TYPE.FORMAT_32: 32}.get(t & IMAGE_TYPE.FORMAT_MASK, 0)
+    return {IMAGE_TYPE.FORMAT_2: 2, IMAGE_TYPE.FORMAT_4: 4, IMAGE_TYPE.FORMAT_8: 8, IMAGE_TYPE.FORMAT_16: 16, IMAGE_TYPE.FORMAT_32: 32}.get(t & IMAGE_TYPE.FORMAT_MASK, 0)
 
 
 def bytes_per_pixel(t: int) -> int:

@@ -50,6 +50,8 @@
 #define T_FLAG_STENCIL (1ull << 25)
 #define T_FLAG_MIPMAPPED (1ull << 27)
 #define T_FLAG_NORMALIZED (1ull << 30)
+#define FMT_2 2u
+#define FMT_4 4u
 #define FMT_8 11u
 #define FMT_16 18u
 #define FMT_32 22u
@@ -67,6 +69,8 @@ static uint32_t format_of(uint64_t t) { return (uint32_t)(t & T_FORMAT_MASK); }
 /* image_types.hpp:541-556: bits per channel for the uniform formats this path supports */
 static uint32_t bits_per_channel(uint64_t t) {
 	switch (format_of(t)) {
+		case FMT_2: return 2; /* FORMAT_2 / FORMAT_4: normalized formats only, channels packed into 1 - 2 bytes (host_image.hpp:341-353) */
+		case FMT_4: return 4;
 		case FMT_8: return 8;
 		case FMT_16: return 16;
 		case FMT_32: return 32;
@@ -238,9 +242,32 @@ static uint64_t texel_offset(const image* img, uint32_t lod, const float coord[3
 	return o;
 }
 
+/* host_image.hpp:333-383 (extract_channels) for FORMAT_2 / FORMAT_4: channel i sits at bits 6 - 2i of byte 0 / in the high (even i) or
+   low nibble of byte i / 2.  Signed formats: the reference's sign fix-up reads
+       if (bpc % 8 != 0 && *((uchannel_type*)&ret[i]) & high_bits[i] != 0u) { ret[i] ^= high_bits[i]; ret[i] = channel_type(-ret[i]); }
+   where `!=` binds tighter than `&`: the test is on bit 0 of the channel, not on its sign bit.  Restated as written (the
+   reference's own build, oracle/_ref, behaves this way: tests/test_reference_pin.py). */
+static int32_t extract_packed(const image* img, const uint8_t* p, uint32_t i) {
+	uint8_t v = img->bpc == 2 ? (uint8_t)((p[0] >> (6u - 2u * i)) & 0x3u) : (uint8_t)((p[i / 2u] >> (i % 2u == 0 ? 4u : 0u)) & 0xFu);
+	if (!img->is_signed) return (int32_t)v;
+	int8_t sv = (int8_t)v;
+	if (v & 1u) {
+		sv = (int8_t)(sv ^ (int8_t)(1u << (img->bpc - 1u)));
+		sv = (int8_t)(-sv);
+	}
+	return (int32_t)sv;
+}
+
 /* host_image.hpp:487-561: decode to float4 (only the stored channels are meaningful) */
 static void decode_float(const image* img, const uint8_t* p, float out[4]) {
 	for (uint32_t i = 0; i < img->channels; ++i) {
+		if (img->bpc < 8) {
+			const uint64_t mask = (1ull << img->bpc) - 1ull;
+			const double den = (double)(img->is_signed ? (mask >> 1) : mask);
+			const float factor = (float)(1.0 / (den > 1.0 ? den : 1.0));
+			out[i] = (float)extract_packed(img, p, i) * factor;
+			continue;
+		}
 		if (img->is_float_data) {
 			if (img->bpc == 32) memcpy(&out[i], p + 4 * i, 4);
 			else { uint16_t h; memcpy(&h, p + 2 * i, 2); out[i] = half_to_float(h); }
@@ -277,6 +304,26 @@ static void decode_int(const image* img, const uint8_t* p, uint32_t out[4]) {
 
 /* host_image.hpp:672-722 + insert_channels :391-460 */
 static void encode_float(const image* img, uint8_t* p, const float c[4]) {
+	if (img->bpc < 8) {
+		/* FORMAT_2 / FORMAT_4 (:421-446): channel_type is 8 bits wide, scale in float, truncate; unsigned keeps the low bits, signed
+		   keeps the low bpc - 1 bits and puts (value < 0) into the channel's top bit; the texel's bytes are cleared first */
+		memset(p, 0, img->bpp);
+		const uint32_t scale_i = (1u << (img->bpc - (img->is_signed ? 1u : 0u))) - 1u;
+		for (uint32_t i = 0; i < img->channels; ++i) {
+			const float scaled = c[i] * (float)scale_i;
+			uint32_t bits;
+			if (!img->is_signed) {
+				const uint8_t q = (uint8_t)scaled; /* channel_type(fp) with channel_type = uint8_t */
+				bits = q & ((1u << img->bpc) - 1u);
+			} else {
+				const int8_t q = (int8_t)scaled;
+				bits = ((uint32_t)q & ((1u << (img->bpc - 1u)) - 1u)) | (q < 0 ? 1u << (img->bpc - 1u) : 0u);
+			}
+			if (img->bpc == 2) p[0] |= (uint8_t)(bits << (6u - 2u * i));
+			else p[i / 2u] |= (uint8_t)(bits << (i % 2u == 0 ? 4u : 0u));
+		}
+		return;
+	}
 	for (uint32_t i = 0; i < img->channels; ++i) {
 		if (img->is_float_data) {
 			if (img->bpc == 32) memcpy(p + 4 * i, &c[i], 4);
@@ -383,6 +430,10 @@ static int image_init(image* img, uint8_t* data, const uint32_t dim[4], uint64_t
 	img->is_signed = dt == T_INT;
 	if (dt == 0) return FLO_ERR_UNSUPPORTED;
 	if (img->is_float_data && img->bpc == 8) return FLO_ERR_UNSUPPORTED;
+	/* FORMAT_2 / FORMAT_4 only exist normalized (host_image.hpp:1167-1186), and only where a texel is a whole number of bytes: the
+	   reference sizes images by bits (image_types.hpp:675-691) but addresses texels by bytes_per_pixel = ceil(bits / 8)
+	   (host_image.hpp:235-271), so R2 / RG2 / RGB2 / R4 / RGB4 images are smaller than what its own kernels touch */
+	if (img->bpc < 8 && (!img->normalized || (img->bpc * img->channels) % 8u != 0u)) return FLO_ERR_UNSUPPORTED;
 	if (type & T_FLAG_DEPTH) { /* only the DEPTH_FLOAT kernels exist (mip_map_minify.hpp:22-30) */
 		if (!(img->is_float_data && img->bpc == 32 && img->channels == 1)) return FLO_ERR_UNSUPPORTED;
 	}
@@ -559,9 +610,13 @@ void flo_fill_synthetic(uint8_t* dst, const uint32_t dim[4], uint64_t type, uint
 						uint32_t layer_num) {
 	uint32_t d0[3];
 	flo_level_dim(dim, type, 0, d0);
-	const uint32_t ch = channel_count(type), bpc = bits_per_channel(type);
-	const uint64_t elems = slice_size(d0, type) / (bpc / 8u);
-	(void)ch;
+	uint32_t bpc = bits_per_channel(type);
+	const uint64_t slice_bytes = slice_size(d0, type);
+	if (bpc < 8) { /* FORMAT_2 / FORMAT_4: the pattern is per storage byte (that of an 8-bit single-channel unorm image of the same bytes) */
+		type = (type & ~(uint64_t)0x3Full & ~(uint64_t)0xC000ull & ~T_DATA_TYPE_MASK) | FMT_8 | T_UINT;
+		bpc = 8;
+	}
+	const uint64_t elems = slice_bytes / (bpc / 8u);
 	for (uint32_t l = 0; l < layer_num; ++l) {
 		uint8_t* p = dst + (uint64_t)l * elems * (bpc / 8u);
 		for (uint64_t e = 0; e < elems; ++e) {

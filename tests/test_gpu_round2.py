@@ -309,3 +309,34 @@ def test_persistent_tma_tile_kernel_plans(gpu_ctx, oracle_mod):
     want_tail = oracle_mod.generate_mip_map_chain(lvl2, (960, 540), t, threads=16)
     assert np.array_equal(got[:o2], full[:o2]) and np.array_equal(got[o2:], want_tail)
     img.destroy()
+
+
+EXTRA_FORMATS = [T.RGB8, T.RGB16, T.RGB8I_NORM, T.RGB16I_NORM, T.RGB8UI, T.RGB8I, T.RGB16UI, T.RGB16I, T.RGB32UI, T.RGB32I, T.RGB16F, T.RGB32F,
+                 T.RGBA2, T.RGBA2I_NORM, T.RG4, T.RG4I_NORM, T.RGBA4, T.RGBA4I_NORM]
+
+
+@pytest.mark.parametrize("fmt", EXTRA_FORMATS)
+def test_three_channel_and_packed_formats(gpu_ctx, oracle_mod, fmt):
+    """3-channel images (the reference's CUDA backend cannot store them in a CUarray, its Host-Compute backend
+    minifies them: host_image.hpp:1167-1210) and the FORMAT_2 / FORMAT_4 normalized formats (host_image.hpp:341-353, 419-446),
+    including the signed variants with the reference's sign fix-up as written.  Linear memory lifts the CUarray restriction; these
+    formats take the literal kernel.  Every dimensionality, POT and NPOT, texel-2 sizes, level limit, both encoder modes."""
+    ctx, dev, q = gpu_ctx
+    for base, dim in [(T.IMAGE_2D, (256, 128)), (T.IMAGE_2D, (100, 37)), (T.IMAGE_2D_ARRAY, (33, 65, 3)), (T.IMAGE_3D, (32, 16, 16)), (T.IMAGE_3D, (12, 10, 6)),
+                      (T.IMAGE_CUBE, (24, 24)), (T.IMAGE_1D, (97,)), (T.IMAGE_1D_ARRAY, (64, 2)), (T.IMAGE_2D, (41, 47)), (T.IMAGE_2D, (64, 4))]:
+        t = base | fmt | M
+        l0 = oracle_mod.fill_synthetic(dim, t, 1200 + (fmt & 0xFFFF))
+        for kw in ({}, {"mip_level_limit": 3}):
+            want = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8, **kw)
+            got, plan = chain(gpu_ctx, l0, dim, t, **kw)
+            assert not plan["single_pass"] and plan["tma_tile_launches"] == 0, plan
+            assert np.array_equal(got, want), (hex(t), dim, kw, int(np.nonzero(got != want)[0][0]))
+        if it.bits_per_channel(t) == 16 and (t & T.FLAG_NORMALIZED):
+            got, _ = chain(gpu_ctx, l0, dim, t, no_double=True)
+            assert np.array_equal(got, oracle_mod.generate_mip_map_chain(l0, dim, t, no_double=True, threads=8)), (hex(t), dim, "no_double")
+    # the device-side synthetic fill defines the same bytes as the oracle's for these formats
+    dim, t = (128, 64, 2), T.IMAGE_2D_ARRAY | fmt | M
+    img = ctx.create_image(q, dim, t)
+    img.fill_synthetic(q, 77, layer_id0=5)
+    assert np.array_equal(img.download_levels(q, 0, 0), oracle_mod.fill_synthetic(dim, t, 77, layer_id0=5))
+    img.destroy()

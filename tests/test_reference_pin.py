@@ -111,7 +111,10 @@ def test_kernel_selection_key(ref_mod):
 FORMATS = [T.R8, T.RG8, T.RGB8, T.RGBA8, T.R16, T.RG16, T.RGBA16, T.R8I_NORM, T.RG8I_NORM, T.RGBA8I_NORM, T.R16I_NORM,
            T.RG16I_NORM, T.RGBA16I_NORM, T.R8UI, T.RG8UI, T.RGBA8UI, T.R8I, T.RG8I, T.RGBA8I, T.R16UI, T.RG16UI, T.RGBA16UI,
            T.R16I, T.RG16I, T.RGBA16I, T.R32UI, T.RG32UI, T.RGBA32UI, T.R32I, T.RG32I, T.RGBA32I,
-           T.R16F, T.RG16F, T.RGB16F, T.RGBA16F, T.R32F, T.RG32F, T.RGB32F, T.RGBA32F]
+           T.R16F, T.RG16F, T.RGB16F, T.RGBA16F, T.R32F, T.RG32F, T.RGB32F, T.RGBA32F,
+           # the remaining 3-channel formats and the FORMAT_2 / FORMAT_4 normalized formats whose texel is a whole number of bytes
+           T.RGB16, T.RGB8I_NORM, T.RGB16I_NORM, T.RGB8UI, T.RGB8I, T.RGB16UI, T.RGB16I, T.RGB32UI, T.RGB32I,
+           T.RGBA2, T.RGBA2I_NORM, T.RG4, T.RG4I_NORM, T.RGBA4, T.RGBA4I_NORM]
 SHAPES = [(T.IMAGE_2D, (64, 64)), (T.IMAGE_2D, (20, 12)), (T.IMAGE_2D, (37, 5)), (T.IMAGE_2D, (129, 67)), (T.IMAGE_2D, (64, 4)),
           (T.IMAGE_2D_ARRAY, (16, 8, 3)), (T.IMAGE_2D_ARRAY, (11, 23, 2)), (T.IMAGE_3D, (16, 16, 16)), (T.IMAGE_3D, (12, 10, 6)),
           (T.IMAGE_3D, (7, 33, 5)), (T.IMAGE_CUBE, (8, 8)), (T.IMAGE_CUBE_ARRAY, (6, 6, 2)),
@@ -260,3 +263,21 @@ def test_reference_golden_fixtures(ref_mod, oracle_mod):
         assert hashlib.sha256(r.tobytes()).hexdigest() == c["chain_sha256"], c["name"]
         o = oracle_mod.generate_mip_map_chain(l0, dim, t, threads=4, **kw)
         assert hashlib.sha256(o.tobytes()).hexdigest() == c["chain_sha256"], c["name"]
+
+
+def test_sub_byte_texels_are_inconsistent_in_the_reference(ref_mod, oracle_mod):
+    """FORMAT_2 / FORMAT_4 formats whose texel is NOT a whole number of bytes (R2, RG2, RGB2, R4, RGB4): the reference sizes the
+    image by bits (image_types.hpp:675-691) but its kernels address texels by bytes_per_pixel = ceil(bits / 8)
+    (host_image.hpp:235-271), so the image is smaller than what the kernels touch.  This path rejects them (flmip.cpp decode_type,
+    oracle image_init); the whole-byte ones (RGBA2, RG4, RGBA4) are supported and pinned above."""
+    import ctypes
+    L = ref_mod.lib()
+    d = (ctypes.c_uint32 * 4)(64, 64, 0, 0)
+    for ch, fmt in [(T.CHANNELS_1, T.FORMAT_2), (T.CHANNELS_2, T.FORMAT_2), (T.CHANNELS_3, T.FORMAT_2), (T.CHANNELS_1, T.FORMAT_4), (T.CHANNELS_3, T.FORMAT_4)]:
+        t = T.IMAGE_2D | ch | fmt | T.UINT | T.FLAG_NORMALIZED | M
+        assert L.flr_level_data_size(d, t, 0) < 64 * 64 * L.flr_bytes_per_pixel(t), hex(t)
+        with pytest.raises(RuntimeError):
+            oracle_mod.generate_mip_map_chain(np.zeros(64 * 64 * 2, np.uint8), (64, 64), t)
+    for fmt in (T.RGBA2, T.RG4, T.RGBA4):
+        t = T.IMAGE_2D | fmt | M
+        assert L.flr_level_data_size(d, t, 0) == 64 * 64 * L.flr_bytes_per_pixel(t) == oracle_mod.level_size((64, 64), t, 0), hex(t)
