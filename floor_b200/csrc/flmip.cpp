@@ -1065,7 +1065,7 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 		im->fast = false;
 		rc = FLMIP_OK;
 	}
-	const bool literal_only = im->channels == 3 || im->elem_kind >= FLMIP_EK_COUNT; // 3-channel and 2 / 4-bit formats
+	const bool literal_only = im->elem_kind >= FLMIP_EK_COUNT; // 2 / 4-bit formats (3-channel images: the LDG tile kernel, never TMA -- 3, 6 and 12-byte texels)
 	if (rc == FLMIP_OK && im->dc >= 2 && !literal_only && ((flags & FLMIP_IMAGE_FORCE_TILED) || !(flags & FLMIP_IMAGE_FORCE_GENERIC))) {
 		char name[64];
 		snprintf(name, sizeof(name), "flmip_tile%ud_k%u_c%u", im->dc, im->elem_kind, im->channels);
@@ -1079,7 +1079,7 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 	// persistent TMA tile kernel for what the single-pass kernel does not take (2D, incl. arrays / cubes): optional, like the
 	// single-pass plan -- when any of its steps fails the LDG tile kernel serves the image
 	static const bool env_no_tma_tiles = env_u32("FLMIP_NO_TMA_TILES", 0) != 0; // A/B tuning runs
-	if (rc == FLMIP_OK && im->tiled && im->dc == 2 && !(flags & FLMIP_IMAGE_NO_TMA_TILES) && !env_no_tma_tiles && populated_levels(*im) > 1u &&
+	if (rc == FLMIP_OK && im->tiled && im->dc == 2 && im->channels != 3 && !(flags & FLMIP_IMAGE_NO_TMA_TILES) && !env_no_tma_tiles && populated_levels(*im) > 1u &&
 		(!im->fast || im->fast_level_count < populated_levels(*im))) {
 		im->tiling = flmip_tiling_lookup(im->bpp, 2);
 		im->sm_count = ds->info.units;

@@ -347,6 +347,16 @@ template <uint32_t EK> struct Codec {
 template <int BPP> struct TexelIO {
 	static constexpr int NW = (BPP + 3) / 4;
 	template <bool CG> static __device__ __forceinline__ void load(const uint8_t* p, uint32_t (&w)[NW]) {
+		if constexpr (BPP == 3) { // 3-channel texels (LDG tile kernel only): element-sized accesses, packed like the other sizes
+			w[0] = (uint32_t)(CG ? __ldcg(p) : p[0]) | (uint32_t)(CG ? __ldcg(p + 1) : p[1]) << 8 | (uint32_t)(CG ? __ldcg(p + 2) : p[2]) << 16;
+		} else if constexpr (BPP == 6) {
+			const unsigned short* h = (const unsigned short*)p;
+			w[0] = (uint32_t)(CG ? __ldcg(h) : h[0]) | (uint32_t)(CG ? __ldcg(h + 1) : h[1]) << 16;
+			w[1] = (uint32_t)(CG ? __ldcg(h + 2) : h[2]);
+		} else if constexpr (BPP == 12) {
+			const uint32_t* q = (const uint32_t*)p;
+			w[0] = CG ? __ldcg(q) : q[0]; w[1] = CG ? __ldcg(q + 1) : q[1]; w[2] = CG ? __ldcg(q + 2) : q[2];
+		} else
 		if constexpr (BPP == 1) { w[0] = CG ? __ldcg(p) : *p; }
 		else if constexpr (BPP == 2) { w[0] = CG ? __ldcg((const unsigned short*)p) : *(const unsigned short*)p; }
 		else if constexpr (BPP == 4) { w[0] = CG ? __ldcg((const uint32_t*)p) : *(const uint32_t*)p; }
@@ -359,6 +369,10 @@ template <int BPP> struct TexelIO {
 		}
 	}
 	static __device__ __forceinline__ void store(uint8_t* p, const uint32_t (&w)[NW]) {
+		if constexpr (BPP == 3) { p[0] = (uint8_t)w[0]; p[1] = (uint8_t)(w[0] >> 8); p[2] = (uint8_t)(w[0] >> 16); }
+		else if constexpr (BPP == 6) { unsigned short* h = (unsigned short*)p; h[0] = (unsigned short)w[0]; h[1] = (unsigned short)(w[0] >> 16); h[2] = (unsigned short)w[1]; }
+		else if constexpr (BPP == 12) { uint32_t* q = (uint32_t*)p; q[0] = w[0]; q[1] = w[1]; q[2] = w[2]; }
+		else
 		if constexpr (BPP == 1) *p = (uint8_t)w[0];
 		else if constexpr (BPP == 2) *(unsigned short*)p = (unsigned short)w[0];
 		else if constexpr (BPP == 4) *(uint32_t*)p = w[0];
@@ -2369,9 +2383,10 @@ FLMIP_PTILE_KERNELS_FOR_KIND(11)
 		tile_body<K, CHN, D>(P);                                                                                                 \
 	}
 #define FLMIP_TILE_KERNELS_FOR_KIND(K) \
-	FLMIP_TILE_KERNEL(2, K, 1) FLMIP_TILE_KERNEL(2, K, 2) FLMIP_TILE_KERNEL(2, K, 4) FLMIP_TILE_KERNEL(3, K, 1) FLMIP_TILE_KERNEL(3, K, 2) FLMIP_TILE_KERNEL(3, K, 4)
+	FLMIP_TILE_KERNEL(2, K, 1) FLMIP_TILE_KERNEL(2, K, 2) FLMIP_TILE_KERNEL(2, K, 4) FLMIP_TILE_KERNEL(3, K, 1) FLMIP_TILE_KERNEL(3, K, 2) FLMIP_TILE_KERNEL(3, K, 4) \
+	FLMIP_TILE_KERNEL(2, K, 3) FLMIP_TILE_KERNEL(3, K, 3) /* 3-channel images: Host-Compute minifies them, a CUarray cannot hold them (cuda_image.cpp:173-180) */
 #ifdef FLMIP_DEV_ONLY
-FLMIP_TILE_KERNEL(2, 2, 4) FLMIP_TILE_KERNEL(2, 1, 4) FLMIP_TILE_KERNEL(3, 0, 1) FLMIP_TILE_KERNEL(2, 0, 4) FLMIP_TILE_KERNEL(3, 1, 4)
+FLMIP_TILE_KERNEL(2, 2, 4) FLMIP_TILE_KERNEL(2, 1, 4) FLMIP_TILE_KERNEL(3, 0, 1) FLMIP_TILE_KERNEL(2, 0, 4) FLMIP_TILE_KERNEL(3, 1, 4) FLMIP_TILE_KERNEL(2, 2, 3) FLMIP_TILE_KERNEL(2, 1, 3) FLMIP_TILE_KERNEL(3, 0, 3)
 #else
 FLMIP_TILE_KERNELS_FOR_KIND(0)
 FLMIP_TILE_KERNELS_FOR_KIND(1)

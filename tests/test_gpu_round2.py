@@ -319,8 +319,8 @@ EXTRA_FORMATS = [T.RGB8, T.RGB16, T.RGB8I_NORM, T.RGB16I_NORM, T.RGB8UI, T.RGB8I
 def test_three_channel_and_packed_formats(gpu_ctx, oracle_mod, fmt):
     """3-channel images (the reference's CUDA backend cannot store them in a CUarray, its Host-Compute backend
     minifies them: host_image.hpp:1167-1210) and the FORMAT_2 / FORMAT_4 normalized formats (host_image.hpp:341-353, 419-446),
-    including the signed variants with the reference's sign fix-up as written.  Linear memory lifts the CUarray restriction; these
-    formats take the literal kernel.  Every dimensionality, POT and NPOT, texel-2 sizes, level limit, both encoder modes."""
+    including the signed variants with the reference's sign fix-up as written.  Linear memory lifts the CUarray restriction:
+    3-channel images take the LDG tile kernel (3 / 6 / 12-byte texels) or, 1D, the literal kernel; the packed formats the literal kernel.  Every dimensionality, POT and NPOT, texel-2 sizes, level limit, both encoder modes."""
     ctx, dev, q = gpu_ctx
     for base, dim in [(T.IMAGE_2D, (256, 128)), (T.IMAGE_2D, (100, 37)), (T.IMAGE_2D_ARRAY, (33, 65, 3)), (T.IMAGE_3D, (32, 16, 16)), (T.IMAGE_3D, (12, 10, 6)),
                       (T.IMAGE_CUBE, (24, 24)), (T.IMAGE_1D, (97,)), (T.IMAGE_1D_ARRAY, (64, 2)), (T.IMAGE_2D, (41, 47)), (T.IMAGE_2D, (64, 4))]:
@@ -331,6 +331,9 @@ def test_three_channel_and_packed_formats(gpu_ctx, oracle_mod, fmt):
             got, plan = chain(gpu_ctx, l0, dim, t, **kw)
             assert not plan["single_pass"] and plan["tma_tile_launches"] == 0, plan
             assert np.array_equal(got, want), (hex(t), dim, kw, int(np.nonzero(got != want)[0][0]))
+            if it.channel_count(t) == 3:  # 3-channel images take the LDG tile kernel (2D / 3D); the literal kernel must agree
+                got, plan = chain(gpu_ctx, l0, dim, t, force_generic=True, **kw)
+                assert np.array_equal(got, want), (hex(t), dim, kw, "literal kernel")
         if it.bits_per_channel(t) == 16 and (t & T.FLAG_NORMALIZED):
             got, _ = chain(gpu_ctx, l0, dim, t, no_double=True)
             assert np.array_equal(got, oracle_mod.generate_mip_map_chain(l0, dim, t, no_double=True, threads=8)), (hex(t), dim, "no_double")
