@@ -794,6 +794,9 @@ ptile_step plan_ptile_step(const flmip_image_s& im, uint32_t src, uint32_t pop) 
 	const bool split = !(im.ptile_flags & FLMIP_IMAGE_TMA_TILES_NO_SPLIT);
 	if (split && src + 2u < pop - 1u) {
 		st.tile_last = st.last = src + 2u;
+		// (Also producing level src + 3 in the consumers -- shuffles between the four threads that hold its source texels -- was built and
+		// measured for 8-byte texels: bit-exact, but N2 0.2305 -> 0.2400 ms: the quarter-occupied warps cost more than the 4x smaller
+		// read of the next launch saves; profiles/r2/04_ptile_experiments.txt.)
 		return st;
 	}
 	st.tile_last = tile_last;
