@@ -6,6 +6,7 @@
 #include <cuda.h> // types and prototypes only -- libcuda is resolved at run time with dlopen/dlsym
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -248,6 +249,58 @@ bool pdl_enabled() {
 	return on;
 }
 
+// ---- overlap of chains on independent images (flmip_stream_set_chain_overlap) ---------------------------------------------------
+// An "open run" of a stream = the images of the chain kernels enqueued on it since the last kernel that waited for its predecessor
+// at its START (pdl_start in mip_kernels.cu).  Only kernels of the open run can still be running when the next kernel's CTAs become
+// resident: a late-waiting kernel starts once the CTAs of the kernel in front of it have all started, and so on back to the kernel
+// that opened the run, whose start implied that everything before it had completed and flushed.  So the first kernel of a chain may
+// skip the wait at its start iff its image is not in the open run; it then waits at its end (completion keeps stream order).
+// Anything else this library enqueues on the stream closes the run (run_close), as does every later kernel of a multi-kernel chain.
+// Opt-in per stream, because work the caller enqueues on the stream behind the library's back cannot be seen here (the caller
+// announces it with flmip_stream_fence).
+struct stream_run {
+	bool enabled = false;
+	std::vector<const void*> images; // compared by address only
+};
+std::mutex runs_mtx;
+std::unordered_map<CUstream, stream_run> runs;
+std::atomic<uint32_t> overlap_streams { 0 }; // streams that have opted in (0: every hook below returns at once)
+constexpr size_t MAX_RUN_IMAGES = 64;
+
+void run_close(CUstream stream) {
+	if (overlap_streams.load(std::memory_order_relaxed) == 0) return;
+	std::lock_guard<std::mutex> lock(runs_mtx);
+	auto it = runs.find(stream);
+	if (it != runs.end()) it->second.images.clear();
+}
+// may the first kernel of a chain on `img` start without waiting for the kernel in front of it?
+bool run_allows_late_head(CUstream stream, const void* img) {
+	if (overlap_streams.load(std::memory_order_relaxed) == 0) return false;
+	std::lock_guard<std::mutex> lock(runs_mtx);
+	auto it = runs.find(stream);
+	if (it == runs.end() || !it->second.enabled) return false;
+	const std::vector<const void*>& v = it->second.images;
+	if (v.empty() || v.size() >= MAX_RUN_IMAGES) return false; // nothing of ours in front / bound the bookkeeping
+	return std::find(v.begin(), v.end(), img) == v.end();
+}
+// after a chain of `kernels` launches on `img`, the first of which started late (or not)
+void run_note_chain(CUstream stream, const void* img, uint32_t kernels, bool late_head) {
+	if (overlap_streams.load(std::memory_order_relaxed) == 0 || kernels == 0) return;
+	std::lock_guard<std::mutex> lock(runs_mtx);
+	auto it = runs.find(stream);
+	if (it == runs.end() || !it->second.enabled) return;
+	if (!(late_head && kernels == 1)) it->second.images.clear(); // an early-waiting kernel opened a new run
+	it->second.images.push_back(img);
+}
+// The chain head's late-wait flag travels to whichever launcher enqueues the chain's first kernel.
+thread_local bool tl_late_head = false;
+thread_local uint32_t tl_chain_launches = 0; // kernels the calling thread has enqueued since flmip_mip_chain_generate_from reset it
+uint32_t take_late_head() {
+	const bool v = tl_late_head;
+	tl_late_head = false;
+	return v ? 1u : 0u;
+}
+
 // While a batch is being built (flmip_batch_create) the launches of the calling thread are recorded as kernel nodes of a CUDA
 // graph instead of being issued: the nodes of one image form a chain, the chains of different images have no edges between them.
 struct graph_recorder {
@@ -295,6 +348,7 @@ int launch(CUfunction fn, uint64_t grid, uint32_t block, uint32_t smem, CUstream
 		CU_TRY(cu.p_cuLaunchKernel(fn, (unsigned)grid, 1, 1, block, 1, 1, smem, stream, args, nullptr), "cuLaunchKernel");
 	}
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
+	++tl_chain_launches;
 	return FLMIP_OK;
 }
 
@@ -689,6 +743,7 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 		T.tiles[2] = im.dc == 3 ? (T.dim[0][2] + FLMIP_TILE3D_Z - 1u) / FLMIP_TILE3D_Z : 1u;
 		T.layers = im.layers;
 		T.no_double = im.no_double;
+		T.late_wait = take_late_head();
 		for (uint32_t k = 2; k <= T.nlev; ++k)
 			for (uint32_t d = 0; d < im.dc; ++d)
 				if (axis_reads_texel_2(im.levels[s + k - 1u].dim[d])) T.block_sync = 1u;
@@ -845,6 +900,7 @@ int launch_ptile(flmip_image_s& im, device_state* ds, uint32_t src, const ptile_
 	P.total_tiles = P.tiles[0] * P.tiles[1] * im.layers;
 	P.stages = 2;
 	P.no_double = im.no_double;
+	P.late_wait = take_late_head();
 	// units of 4 tiles (one publish per unit) once every resident CTA has many tiles to work through; below that the pool keeps up
 	// with one publish per tile, and units would only coarsen what the scheduler can balance
 	const uint64_t resident_ctas = 2ull * ds->info.units;
@@ -935,12 +991,39 @@ int flmip_stream_destroy(int device, flmip_stream stream) {
 			im->last_stream = nullptr;
 		}
 	}
+	{
+		std::lock_guard<std::mutex> lock(runs_mtx);
+		auto it = runs.find((CUstream)stream);
+		if (it != runs.end()) {
+			if (it->second.enabled) overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+			runs.erase(it);
+		}
+	}
 	CU_TRY(cu.p_cuStreamDestroy((CUstream)stream), "cuStreamDestroy");
 	return FLMIP_OK;
 }
 int flmip_stream_sync(int device, flmip_stream stream) {
 	WITH_DEVICE(device)
 	CU_TRY(cu.p_cuStreamSynchronize((CUstream)stream), "cuStreamSynchronize");
+	return FLMIP_OK;
+}
+int flmip_stream_set_chain_overlap(int device, flmip_stream stream, int enable) {
+	WITH_DEVICE(device)
+	(void)ds;
+	std::lock_guard<std::mutex> lock(runs_mtx);
+	stream_run& r = runs[(CUstream)stream];
+	if ((enable != 0) != r.enabled) {
+		r.enabled = enable != 0;
+		if (r.enabled) overlap_streams.fetch_add(1, std::memory_order_relaxed);
+		else overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+	}
+	r.images.clear();
+	return FLMIP_OK;
+}
+int flmip_stream_fence(int device, flmip_stream stream) {
+	WITH_DEVICE(device)
+	(void)ds;
+	run_close((CUstream)stream);
 	return FLMIP_OK;
 }
 int flmip_event_create(int device, flmip_event* out) {
@@ -952,6 +1035,7 @@ int flmip_event_create(int device, flmip_event* out) {
 	return FLMIP_OK;
 }
 int flmip_event_record(int device, flmip_event ev, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	WITH_DEVICE(device)
 	CU_TRY(cu.p_cuEventRecord((CUevent)ev, (CUstream)stream), "cuEventRecord");
 	return FLMIP_OK;
@@ -1148,9 +1232,12 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 int order_after_previous_chain(flmip_image_s& im, CUstream stream) {
 	if (tl_recorder) return FLMIP_OK; // recording a batch graph: flmip_batch_generate orders the graph launch
 	if (im.pending_handover) {
+		run_close(stream);
 		CU_TRY(cu.p_cuStreamWaitEvent(stream, im.handover, 0), "cuStreamWaitEvent(chain hand-over)");
 		im.pending_handover = false;
 	} else if (im.has_last && im.last_stream != stream) {
+		run_close(stream);
+		run_close(im.last_stream);
 		if (!im.handover) CU_TRY(cu.p_cuEventCreate(&im.handover, CU_EVENT_DISABLE_TIMING), "cuEventCreate(chain hand-over)");
 		CU_TRY(cu.p_cuEventRecord(im.handover, im.last_stream), "cuEventRecord(chain hand-over)");
 		CU_TRY(cu.p_cuStreamWaitEvent(stream, im.handover, 0), "cuStreamWaitEvent(chain hand-over)");
@@ -1271,6 +1358,7 @@ int flmip_image_plan_tma_tile_launches(flmip_image img, uint32_t* out) {
 }
 
 int flmip_image_upload(flmip_image img, const void* src, size_t src_size, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	if (!src) return fail(FLMIP_ERR_INVALID, "null source");
 	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
@@ -1283,6 +1371,7 @@ int flmip_image_upload(flmip_image img, const void* src, size_t src_size, uint32
 }
 
 int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	if (!dst) return fail(FLMIP_ERR_INVALID, "null destination");
 	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
@@ -1296,6 +1385,7 @@ int flmip_image_download(flmip_image img, void* dst, size_t dst_size, uint32_t l
 
 int flmip_image_download_layers(flmip_image img, void* dst, size_t dst_size, uint32_t level_first, uint32_t level_last, uint32_t layer_first,
 								uint32_t layer_count, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	if (!dst) return fail(FLMIP_ERR_INVALID, "null destination");
 	if (level_first > level_last || level_last >= img->level_count) return fail(FLMIP_ERR_INVALID, "invalid mip level range [%u, %u]", level_first, level_last);
@@ -1318,6 +1408,7 @@ int flmip_image_download_layers(flmip_image img, void* dst, size_t dst_size, uin
 
 int flmip_image_write(flmip_image img, const void* src, size_t src_size, const uint32_t offset[3], const uint32_t extent[3],
 					  const uint32_t mip_level_range[2], const uint32_t layer_range[2], flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	if (!src || !offset || !extent || !mip_level_range || !layer_range) return fail(FLMIP_ERR_INVALID, "null argument");
 	// write_check (device_image.cpp:503-547)
@@ -1389,6 +1480,7 @@ int flmip_image_write(flmip_image img, const void* src, size_t src_size, const u
 }
 
 int flmip_image_zero(flmip_image img, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	WITH_DEVICE(img->device)
 	CU_TRY(cu.p_cuMemsetD8Async(img->mem, 0, img->total_size, (CUstream)stream), "cuMemsetD8Async");
@@ -1398,6 +1490,7 @@ int flmip_image_zero(flmip_image img, flmip_stream stream) {
 // -- blit / clone support: device_image::blit (device_image.hpp:96-101; CUDA inherits the `return false` stub, so
 //    clone(copy_contents = true) copies nothing there) -- on linear images it is one device-to-device copy.
 int flmip_image_blit(flmip_image dst, flmip_image src, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(dst) || check_image(src)) return FLMIP_ERR_INVALID;
 	// blit_check (device_image.cpp:470-501): identical dim, layer count, size and format; no compressed formats
 	if (memcmp(dst->dim, src->dim, sizeof(dst->dim)) != 0) return fail(FLMIP_ERR_INVALID, "blit: dim mismatch");
@@ -1473,6 +1566,7 @@ enum class tiled_dir { to_tiled, from_tiled, tiled_to_host };
 // one cuMemcpy3DAsync per level: rows x height x (depth | layers) between the level-major linear layout and the level's CUarray
 int tiled_copy(flmip_image img, void* mipmapped_array, uint32_t level_first, uint32_t level_last, tiled_dir dir, void* host, size_t host_size,
 			   CUstream stream) {
+	run_close(stream);
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	if (!mipmapped_array) return fail(FLMIP_ERR_INVALID, "null array");
 	if (img->dc < 2) return fail(FLMIP_ERR_UNSUPPORTED, "tiled interop covers 2D, 2D-array, cube, cube-array and 3D images");
@@ -1529,13 +1623,27 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 		const int rc = order_after_previous_chain(*img, (CUstream)stream);
 		if (rc != FLMIP_OK) return rc;
 	}
+	// chain overlap (opt-in per stream): the first kernel of this chain may start without waiting for the kernel in front of it when
+	// that one belongs to a chain on another image; only the PDL kernels know how (not the literal kernel, not a recorded graph)
+	const bool head_is_pdl_kernel = (img->fast && first_level == 0) || img->tiled;
+	const bool late_head = head_is_pdl_kernel && !tl_recorder && pdl_enabled() && run_allows_late_head((CUstream)stream, img);
+	tl_late_head = late_head;
+	tl_chain_launches = 0;
+	struct chain_note {
+		flmip_image img; CUstream stream; bool late;
+		~chain_note() {
+			tl_late_head = false;
+			if (!tl_recorder) run_note_chain(stream, img, tl_chain_launches, late);
+		}
+	} note { img, (CUstream)stream, late_head };
 	uint32_t next = first_level + 1; // first level still to be produced
 	if (img->fast && first_level == 0) {
 		CUfunction fn = nullptr;
 		int rc = get_function(ds, img->fast_name, img->fast_smem, &fn);
 		if (rc != FLMIP_OK) return rc;
-		const flmip_fast_params& P = img->fast_params;
-		void* args[] = { &img->tmap, const_cast<flmip_fast_params*>(&P) };
+		flmip_fast_params P = img->fast_params;
+		P.late_wait = take_late_head();
+		void* args[] = { &img->tmap, &P };
 		rc = launch(fn, img->fast_grid, FLMIP_BLOCK_THREADS, img->fast_smem, (CUstream)stream, args, true);
 		if (rc != FLMIP_OK) return rc;
 		next = img->fast_level_count;
@@ -1604,6 +1712,7 @@ int flmip_batch_create(const flmip_image* images, uint32_t count, flmip_batch* o
 }
 
 int flmip_batch_generate(flmip_batch batch, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (!batch) return fail(FLMIP_ERR_INVALID, "null batch handle");
 	if (!batch->exec) return FLMIP_OK; // nothing to generate (single-level images)
 	WITH_DEVICE(batch->device)
@@ -1647,6 +1756,7 @@ extern "C" int flmip_debug_timeline(flmip_image img, uint64_t* out, uint32_t cta
 #endif
 
 int flmip_image_fill_synthetic(flmip_image img, uint64_t config_id, uint64_t layer_id0, flmip_stream stream) {
+	run_close((CUstream)stream); // chain overlap: anything but a chain kernel ends the stream's open run
 	if (check_image(img)) return FLMIP_ERR_INVALID;
 	WITH_DEVICE(img->device)
 	flmip_fill_params F;

@@ -583,6 +583,17 @@ __device__ __forceinline__ void pdl_wait_then_release() {
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Chains of independent images (`late_wait`, set by the host when the kernel before this one in the stream is a chain on ANOTHER image and
+// the queue has opted in: flmip_stream_set_chain_overlap): nothing this kernel reads or writes is touched by its predecessor, so it starts
+// streaming while that kernel's tail (last units, group / layer stages: 7 - 10 us without memory traffic) is still running, and its own
+// dependents may follow as soon as its CTAs are resident.  Stream order for whatever comes after is kept by waiting for the predecessor
+// at the END instead (pdl_late_wait, one thread of one CTA: a grid is complete when its last CTA is), so a grid never completes before
+// the grid in front of it has completed and flushed.
+__device__ __forceinline__ void pdl_start(uint32_t late_wait) {
+	if (late_wait) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	else pdl_wait_then_release();
+}
+__device__ __forceinline__ void pdl_late_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 #ifdef FLMIP_TIMELINE
 // tuning builds only (make DEFS=-DFLMIP_TIMELINE): per-CTA time stamps behind the scheduler words, read back by flmip_debug_timeline
@@ -868,7 +879,7 @@ __device__ __forceinline__ void fast_body(const CUtensorMap& tmap, const flmip_f
 		fence_mbar_init();
 	}
 	__syncthreads();
-	pdl_wait_then_release();
+	pdl_start(P.late_wait);
 	if (tid == 0) FLMIP_STAMP(P, 0); // CTA may touch global memory from here
 
 	constexpr uint32_t SLOT_BYTES = TL::CASCADE_BYTES + TL::CASCADE_BYTES / 4u;
@@ -1470,7 +1481,7 @@ __device__ __forceinline__ void tile_body(const flmip_tile_params& P) {
 		}
 	}
 	__syncthreads();
-	pdl_wait_then_release();
+	pdl_start(P.late_wait);
 
 	// ---- level 1: straight from global memory (each warp reads whole 2 * BPP * 32 byte row segments) -------------
 	// 2D: warp w owns rows 4w .. 4w+3 of level 1 (so that levels 2 and 3 stay inside the warp); 3D: o = t + c * 256
@@ -1825,7 +1836,7 @@ __device__ __forceinline__ void ptile_body(const CUtensorMap& tmap, const flmip_
 		fence_mbar_init();
 	}
 	__syncthreads();
-	pdl_wait_then_release();
+	pdl_start(P.late_wait);
 	if (tid == 0) FLMIP_STAMP(P, 0); // CTA may touch global memory from here
 
 	// the finisher pool is idle when the consumers' in-register levels end the launch
@@ -2318,6 +2329,7 @@ extern "C" __global__ void __launch_bounds__(256) flmip_fill(const __grid_consta
 	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_fast##D##d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,    \
 																					   const __grid_constant__ flmip_fast_params P) { \
 		fast_body<K, CHN, D>(tmap, P);                                                                                          \
+		if (P.late_wait && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                                \
 	}
 #define FLMIP_FAST_KERNELS_FOR_KIND(K) \
 	FLMIP_FAST_KERNEL(2, K, 1) FLMIP_FAST_KERNEL(2, K, 2) FLMIP_FAST_KERNEL(2, K, 4) FLMIP_FAST_KERNEL(3, K, 1) FLMIP_FAST_KERNEL(3, K, 2) FLMIP_FAST_KERNEL(3, K, 4)
@@ -2344,6 +2356,7 @@ FLMIP_FAST_KERNELS_FOR_KIND(11)
 	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_ptile2d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,     \
 																							   const __grid_constant__ flmip_ptile_params P) { \
 		ptile_body<K, CHN>(tmap, P);                                                                                                \
+		if (P.late_wait && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                                    \
 	}
 #define FLMIP_PTILE_KERNELS_FOR_KIND(K) FLMIP_PTILE_KERNEL(K, 1) FLMIP_PTILE_KERNEL(K, 2) FLMIP_PTILE_KERNEL(K, 4)
 #ifdef FLMIP_DEV_ONLY
@@ -2381,6 +2394,7 @@ FLMIP_PTILE_KERNELS_FOR_KIND(11)
 #define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
 	extern "C" __global__ void __launch_bounds__(256, FLMIP_TILE_MIN_BLOCKS(D, K, CHN)) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
 		tile_body<K, CHN, D>(P);                                                                                                 \
+		if (P.late_wait && blockIdx.x == gridDim.x - 1u && threadIdx.x == 0) pdl_late_wait();                                    \
 	}
 #define FLMIP_TILE_KERNELS_FOR_KIND(K) \
 	FLMIP_TILE_KERNEL(2, K, 1) FLMIP_TILE_KERNEL(2, K, 2) FLMIP_TILE_KERNEL(2, K, 4) FLMIP_TILE_KERNEL(3, K, 1) FLMIP_TILE_KERNEL(3, K, 2) FLMIP_TILE_KERNEL(3, K, 4) \

@@ -69,6 +69,7 @@ struct flmip_fast_params {
 	uint32_t layers, level_count, no_double;
 	uint32_t total_units;   // units per layer * layers, handed out by the dynamic scheduler
 	uint32_t stages;        // depth of the TMA tile ring in shared memory (<= FLMIP_MAX_STAGES)
+	uint32_t late_wait;     // set per launch: the kernel before this one in the stream is a chain on another image (pdl_start / pdl_late_wait)
 };
 
 // multi-level tile kernel, any size (NPOT capable): one CTA reduces one source tile of level [0] through `nlev` levels.
@@ -92,6 +93,7 @@ struct flmip_tile_params {
 	uint32_t tiles[3];                         // source tiles per layer
 	uint32_t nlev, layers, no_double;
 	uint32_t block_sync; // 1: some produced level >= 2 contains a texel-2 fetch (block barriers instead of warp barriers)
+	uint32_t late_wait;  // as in flmip_fast_params
 };
 
 // persistent TMA tile kernel, 2D images of any size whose source rows are 16-byte multiples (flmip_ptile2d_*): the single-pass
@@ -122,6 +124,7 @@ struct flmip_ptile_params {
 	uint32_t tiles[2], layers, total_tiles, stages, no_double;
 	uint32_t unit_shift;                  // log2(tiles per unit): 2 when every CTA has many tiles (one publish per 4 tiles), else 0
 	uint32_t vec1, vec2;                  // rows of level src + 1 / src + 2 start on 16- / 8-byte (16-byte texels: 16-byte) boundaries: full-width vector stores
+	uint32_t late_wait;                   // as in flmip_fast_params
 };
 
 struct flmip_fill_params {

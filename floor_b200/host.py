@@ -108,6 +108,14 @@ class device_queue:
     def flush(self):
         pass
 
+    def set_mip_chain_overlap(self, enable: bool = True):
+        """chains on independent images overlap on this queue (flmip_stream_set_chain_overlap; no counterpart in the reference)"""
+        _check(_L().flmip_stream_set_chain_overlap(self.dev.index, self._stream, 1 if enable else 0))
+
+    def fence(self):
+        """announces work enqueued on get_queue_ptr() behind the library's back (flmip_stream_fence)"""
+        _check(_L().flmip_stream_fence(self.dev.index, self._stream))
+
     # -- profiling with CUDA events on this queue's stream (cuda_queue.cpp:58-70) --
     def record_event(self):
         ev = ctypes.c_void_p()

@@ -108,6 +108,12 @@ public:
 		if (flmip_stream_sync(dev.device_id, stream) != FLMIP_OK) FLB_LOG_ERROR("queue finish failed: %s", flmip_last_error_string());
 	}
 	void flush() const {}
+	//! not in the reference: chains on independent images enqueued on this queue overlap (flmip_stream_set_chain_overlap); work enqueued on
+	//! get_queue_ptr() behind the library's back must then be announced with fence() before the next chain
+	void set_mip_chain_overlap(const bool enable) const {
+		if (flmip_stream_set_chain_overlap(dev.device_id, stream, enable ? 1 : 0) != FLMIP_OK) FLB_LOG_ERROR("set_mip_chain_overlap failed: %s", flmip_last_error_string());
+	}
+	void fence() const { flmip_stream_fence(dev.device_id, stream); }
 	const void* get_queue_ptr() const { return stream; }
 	void* get_queue_ptr() { return stream; }
 	const cuda_device& get_device() const { return dev; }
