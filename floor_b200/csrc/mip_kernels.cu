@@ -675,6 +675,23 @@ __device__ __forceinline__ void gather_region(uint8_t* smem_dst, const Region& R
 	const uint32_t sw = 31u - __clz(R.w), sh = 31u - __clz(R.h);
 	const uint8_t* g = level_layer_ptr<BPP, DIMS>(P, R.lvl, layer);
 	const uint32_t n = R.w * R.h * R.d;
+	{
+		// rows of the region that are whole, aligned 16-byte vectors (the group patches of every benchmarked shape): asynchronous 16-byte
+		// copies L2 -> shared memory, all of them in flight at once and none of them through registers -- one round trip where the texel
+		// loop below needs up to four batches (C5: 4 KB per group patch)
+		const uint32_t row_bytes = R.w * BPP;
+		if ((row_bytes & 15u) == 0u && ((reinterpret_cast<uint64_t>(g) | ((uint64_t)LW * BPP) | ((uint64_t)R.ox * BPP)) & 15u) == 0u) {
+			const uint32_t vsh = 31u - __clz(row_bytes >> 4), nv = (n * BPP) >> 4;
+			for (uint32_t i = lane; i < nv; i += 32u) {
+				const uint32_t vx = i & ((1u << vsh) - 1u), row = i >> vsh, y = row & (R.h - 1u), z = row >> sh;
+				const uint8_t* src = g + ((uint64_t)(R.oz + z) * LH * LW + (uint64_t)(R.oy + y) * LW + R.ox) * BPP + (size_t)vx * 16u;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst + (size_t)i * 16u)), "l"(src) : "memory");
+			}
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			__syncwarp();
+			return;
+		}
+	}
 	for (uint32_t base = 0; base < n; base += 32u * U) {
 		uint32_t t[U][IO::NW];
 #pragma unroll
