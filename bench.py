@@ -293,6 +293,16 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
         for i in range(max(warmup, n_pipe)):
             rot[i % n_pipe].enqueue_mip_map_chain(qo)
         ranks.barrier(qo)
+        # A host thread needs 5 - 8 us to enqueue a chain (Python + cuLaunchKernelEx), which is more than the GPU needs for an overlapped
+        # chain of the small workloads (c1: ~4 us): their steps are enqueued behind ~3 ms of untimed work on the same queue (chains on a
+        # 716 MB image), so that the events bracket what the GPU does with the queued steps and not the enqueue loop.
+        blocker = None
+        if alg_bytes < 64e6:
+            blocker = ctx.create_image(qo, (8192, 8192), T.IMAGE_2D | T.RGBA16F | T.FLAG_MIPMAPPED | T.READ_WRITE)
+            blocker.fill_synthetic(qo, 2, 0)
+            qo.finish()
+            for _ in range(28):
+                blocker.enqueue_mip_map_chain(qo)
         p0 = qo.record_event()
         for i in range(steps):
             rot[(i + 1) % n_pipe].enqueue_mip_map_chain(qo)
@@ -307,6 +317,9 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
                              "first kernel streams while the previous chain's tail finishes; completion still follows stream order); "
                              "value / roofline above are the strictly stream-ordered numbers"}
         qo.finish()
+        if blocker is not None:
+            pipelined["note"] += "; the steps of this small workload are enqueued behind ~3 ms of untimed work so that the events time the device, not the host's enqueue loop"
+            blocker.destroy()
         qo.destroy()
     # what did the timed launches write?  image 1 % n_rot was the first one of the timed loop (both legs)
     chk_i = 1 % n_rot

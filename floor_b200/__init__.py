@@ -25,7 +25,7 @@ HOST_WRITE_COMBINED = 1
 # every symbol include/floor_b200_mip.h declares (checked by tests/test_cabi.py without a GPU)
 EXPORTS = [
     "flmip_init", "flmip_device_count", "flmip_get_device_info", "flmip_last_error_string", "flmip_launch_count",
-    "flmip_stream_create", "flmip_stream_destroy", "flmip_stream_sync", "flmip_stream_set_chain_overlap", "flmip_stream_fence",
+    "flmip_stream_create", "flmip_stream_destroy", "flmip_stream_sync", "flmip_stream_set_chain_overlap", "flmip_stream_fence", "flmip_overlap_bookkeeping",
     "flmip_event_create", "flmip_event_record", "flmip_event_sync", "flmip_event_elapsed_ms", "flmip_event_destroy",
     "flmip_host_alloc", "flmip_host_alloc_ex", "flmip_host_free",
     "flmip_device_attach_context", "flmip_image_create_external", "flmip_image_download_layers",
@@ -96,6 +96,7 @@ def lib() -> ctypes.CDLL:
         "flmip_stream_sync": (i32, [i32, vp]),
         "flmip_stream_set_chain_overlap": (i32, [i32, vp, i32]),
         "flmip_stream_fence": (i32, [i32, vp]),
+        "flmip_overlap_bookkeeping": (i32, [u64, u64, ctypes.c_uint32, ctypes.c_uint32]),
         "flmip_event_create": (i32, [i32, ctypes.POINTER(vp)]),
         "flmip_event_record": (i32, [i32, vp, vp]),
         "flmip_event_sync": (i32, [i32, vp]),

@@ -571,7 +571,7 @@ int plan_fast(flmip_image_s& im, device_state* ds, uint32_t flags) {
 	// counters: one per tile group and one per layer, zeroed once; the kernel resets what it uses
 	const uint64_t n_groups = (uint64_t)im.layers * P.groups[0] * P.groups[1] * P.groups[2];
 #ifdef FLMIP_TIMELINE
-	const uint64_t n_counters = n_groups + im.layers + 2u + 4u + 2u * 4u * 1024u; // + 4 x u64 per CTA behind the scheduler words (tuning builds)
+	const uint64_t n_counters = n_groups + im.layers + 2u + 4u + 2u * 8u * 1024u; // + 8 x u64 per CTA behind the scheduler words (tuning builds)
 #else
 	const uint64_t n_counters = n_groups + im.layers + 2u /* scheduler */;
 #endif
@@ -991,14 +991,7 @@ int flmip_stream_destroy(int device, flmip_stream stream) {
 			im->last_stream = nullptr;
 		}
 	}
-	{
-		std::lock_guard<std::mutex> lock(runs_mtx);
-		auto it = runs.find((CUstream)stream);
-		if (it != runs.end()) {
-			if (it->second.enabled) overlap_streams.fetch_sub(1, std::memory_order_relaxed);
-			runs.erase(it);
-		}
-	}
+	flmip_overlap_bookkeeping(reinterpret_cast<uint64_t>(stream), 0, 4, 0);
 	CU_TRY(cu.p_cuStreamDestroy((CUstream)stream), "cuStreamDestroy");
 	return FLMIP_OK;
 }
@@ -1010,15 +1003,44 @@ int flmip_stream_sync(int device, flmip_stream stream) {
 int flmip_stream_set_chain_overlap(int device, flmip_stream stream, int enable) {
 	WITH_DEVICE(device)
 	(void)ds;
-	std::lock_guard<std::mutex> lock(runs_mtx);
-	stream_run& r = runs[(CUstream)stream];
-	if ((enable != 0) != r.enabled) {
-		r.enabled = enable != 0;
-		if (r.enabled) overlap_streams.fetch_add(1, std::memory_order_relaxed);
-		else overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+	return flmip_overlap_bookkeeping(reinterpret_cast<uint64_t>(stream), 0, 0, enable != 0);
+}
+// The bookkeeping above is plain host logic: this hook lets the CPU tests drive it without a GPU.  op 0: opt `stream` in / out (arg = 0 / 1);
+// op 1: a chain of `arg` kernels on `image` whose first kernel is a PDL kernel -- returns 1 if that kernel would start late; op 2: a chain
+// whose first kernel is the literal kernel (never late); op 3: anything else enqueued on the stream; op 4: forget the stream.
+int flmip_overlap_bookkeeping(uint64_t stream, uint64_t image, uint32_t op, uint32_t arg) {
+	const CUstream s = reinterpret_cast<CUstream>(stream);
+	const void* img = reinterpret_cast<const void*>(image);
+	switch (op) {
+		case 0: {
+			std::lock_guard<std::mutex> lock(runs_mtx);
+			stream_run& r = runs[s];
+			if ((arg != 0) != r.enabled) {
+				r.enabled = arg != 0;
+				if (r.enabled) overlap_streams.fetch_add(1, std::memory_order_relaxed);
+				else overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+			}
+			r.images.clear();
+			return 0;
+		}
+		case 1:
+		case 2: {
+			const bool late = op == 1 && run_allows_late_head(s, img);
+			run_note_chain(s, img, arg, late);
+			return late ? 1 : 0;
+		}
+		case 3: run_close(s); return 0;
+		case 4: {
+			std::lock_guard<std::mutex> lock(runs_mtx);
+			auto it = runs.find(s);
+			if (it != runs.end()) {
+				if (it->second.enabled) overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+				runs.erase(it);
+			}
+			return 0;
+		}
+		default: return fail(FLMIP_ERR_INVALID, "unknown bookkeeping op %u", op);
 	}
-	r.images.clear();
-	return FLMIP_OK;
 }
 int flmip_stream_fence(int device, flmip_stream stream) {
 	WITH_DEVICE(device)
@@ -1181,7 +1203,7 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 		if (prc == FLMIP_OK) prc = build_sampler_table(*im, ds);
 		if (prc == FLMIP_OK) {
 #ifdef FLMIP_TIMELINE
-			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 4u * 1024u; // + 4 x u64 per CTA behind the scheduler words (tuning builds)
+			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 8u * 1024u; // + 4 x u64 per CTA behind the scheduler words (tuning builds)
 #else
 			const size_t n_pc = (size_t)im->layers + 2u;
 #endif
@@ -1190,7 +1212,7 @@ int create_image_impl(int device, uint64_t image_type, const uint32_t image_dim[
 		}
 		if (prc == FLMIP_OK) {
 #ifdef FLMIP_TIMELINE
-			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 4u * 1024u;
+			const size_t n_pc = (size_t)im->layers + 2u + 4u + 2u * 8u * 1024u;
 #else
 			const size_t n_pc = (size_t)im->layers + 2u;
 #endif
@@ -1748,9 +1770,9 @@ extern "C" int flmip_debug_timeline(flmip_image img, uint64_t* out, uint32_t cta
 	WITH_DEVICE(img->device)
 	const uint64_t sched = img->fast ? img->fast_params.sched : img->pcounters + (uint64_t)img->layers * sizeof(uint32_t);
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((sched + 15ull) & ~7ull), (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((sched + 15ull) & ~7ull), (size_t)ctas * 8u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemsetD8Async(((sched + 15ull) & ~7ull), 0, (size_t)ctas * 4u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
+	CU_TRY(cu.p_cuMemsetD8Async(((sched + 15ull) & ~7ull), 0, (size_t)ctas * 8u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
 	return FLMIP_OK;
 }
 #endif

@@ -602,8 +602,8 @@ __device__ __forceinline__ uint64_t gtime() {
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
-#define FLMIP_STAMP(P, slot) (reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 4u + (slot)] = gtime())
-#define FLMIP_STAMP_MAX(P, slot) atomicMax(&reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 4u + (slot)], (unsigned long long)gtime())
+#define FLMIP_STAMP(P, slot) (reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 8u + (slot)] = gtime())
+#define FLMIP_STAMP_MAX(P, slot) atomicMax(&reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 8u + (slot)], (unsigned long long)gtime())
 #else
 #define FLMIP_STAMP(P, slot) ((void)0)
 #define FLMIP_STAMP_MAX(P, slot) ((void)0)
@@ -822,6 +822,7 @@ __device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b,
 	const uint32_t layer = tc.layer;
 	const GroupOf<BPP, DIMS> grp(P, tc);
 
+	if (lane == 0) FLMIP_STAMP_MAX(P, 4); // last arriver of a group: its publish has returned
 	if (lane == 0) {
 		while (atomicCAS(patch_lock, 0u, 1u) != 0u) __nanosleep(64);
 	}
@@ -831,7 +832,9 @@ __device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b,
 	R.w *= grp.ntx; R.h *= grp.nty; R.d *= grp.ntz;
 	uint8_t *src = patch_a, *dst = patch_b;
 	gather_region<BPP, DIMS>(src, R, P, layer, lane);
+	if (lane == 0) FLMIP_STAMP_MAX(P, 5); // group patch gathered
 	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+	if (lane == 0) FLMIP_STAMP_MAX(P, 6); // group patch reduced
 
 	// ---- layer stage: the last group of a layer finishes the chain -----------------------------------------
 	const uint32_t groups_per_layer = P.groups[0] * P.groups[1] * P.groups[2];
@@ -842,6 +845,7 @@ __device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b,
 		src = patch_a; dst = patch_b;
 		gather_region<BPP, DIMS>(src, R, P, layer, lane);
 		cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+		if (lane == 0) FLMIP_STAMP_MAX(P, 7); // layer stage done: the chain of this layer is complete
 	}
 	__syncwarp();
 	if (lane == 0) {

@@ -90,6 +90,10 @@ int flmip_stream_sync(int device, flmip_stream stream);
  * default).  Measured on a B200 (chains of different images back to back): 8192^2 RGBA16F 111.7 -> 102.5 us, 1024^2 RGBA8 10.5 -> 3.9 us. */
 int flmip_stream_set_chain_overlap(int device, flmip_stream stream, int enable);
 int flmip_stream_fence(int device, flmip_stream stream);
+/* test hook (no GPU needed): drives the host bookkeeping behind the overlap -- op 0: opt `stream` in / out (arg), 1: a chain of `arg`
+ * kernels on `image` (returns 1 if its first kernel would start without waiting), 2: the same for a chain the literal kernel starts,
+ * 3: anything else enqueued on the stream, 4: forget the stream */
+int flmip_overlap_bookkeeping(uint64_t stream, uint64_t image, uint32_t op, uint32_t arg);
 /* profiling: cuda_queue::start_profiling / stop_profiling (cuda_queue.cpp:58-70) */
 int flmip_event_create(int device, flmip_event* out);
 int flmip_event_record(int device, flmip_event ev, flmip_stream stream);

@@ -9,7 +9,9 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $out/box.t
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
 tail -3 $out/pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -1 $out/smoke.log
+t0=$SECONDS
 timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_default.json 2> $out/bench_default.err; cut -c1-300 $out/bench_default.json
+echo "default bench.py line: $((SECONDS - t0)) s wall" | tee $out/bench_default.time
 for w in c1 c5 c3 c4 n1 n2; do
   timeout 900 python bench.py --workload $w --steps 20 --warmup 5 > $out/bench_$w.json 2> $out/bench_$w.err; cut -c1-200 $out/bench_$w.json
 done

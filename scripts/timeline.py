@@ -18,7 +18,7 @@ for name, dim, t in [("c2", (8192, 8192), T.IMAGE_2D | T.RGBA16F | M), ("c5", (5
         imgs[k & 1].enqueue_mip_map_chain(q)
     q.finish()
     n = 296
-    buf = np.zeros((n, 4), np.uint64)
+    buf = np.zeros((n, 8), np.uint64)
     L.flmip_debug_timeline(imgs[0]._handle, buf.ctypes.data, n)   # clears the stamps
     e0 = q.record_event()
     imgs[0].enqueue_mip_map_chain(q)
@@ -35,5 +35,13 @@ for name, dim, t in [("c2", (8192, 8192), T.IMAGE_2D | T.RGBA16F | M), ("c5", (5
     print(f"   consumers done       {f(rel[:, 2])}")
     print(f"   last finisher done   {f(rel[:, 3])}")
     print(f"   histogram of 'last finisher done' (us): {np.histogram(rel[:, 3], bins=8)[0].tolist()} edges {np.round(np.histogram(rel[:, 3], bins=8)[1], 1).tolist()}")
+    # last-arriver stages (only the CTAs that ran one have these stamps): publish returned, patch gathered, patch reduced, layer stage done
+    stages = rel[:, 4:8]
+    ran = live[:, 4] != 0
+    if ran.any():
+        order = np.argsort(rel[ran][:, 6])[-4:]
+        for row in rel[ran][order]:
+            print(f"   group stage of a CTA: consumers done {row[2]:7.1f} | publish returned {row[4]:7.1f} gathered {row[5]:7.1f} reduced {row[6]:7.1f}"
+                  + (f" | layer stage done {row[7]:7.1f}" if row[7] > 0 else ""))
     for im in imgs:
         im.destroy()

@@ -182,6 +182,27 @@ int main(int argc, char** argv) {
 			CHECK(imgs[i]->read_levels(*queue, got.data(), got.size(), 0, imgs[i]->get_mip_level_count() - 1));
 			CHECK(got == wants[i]);
 		}
+		// the same textures as overlapping chains on one queue (device_queue::set_mip_chain_overlap): zeroed first, so every level read
+		// back below was written by these chains
+		queue->set_mip_chain_overlap(true);
+		for (int rep = 0; rep < 3; ++rep) {
+			for (size_t i = 0; i < imgs.size(); ++i) {
+				const size_t l0_size = image_data_size_from_types(imgs[i]->get_image_dim(), imgs[i]->get_image_type(), true);
+				CHECK(imgs[i]->zero(*queue));
+				const uint4 d = imgs[i]->get_image_dim();
+				const uint3 extent { d.x, d.y, image_dim_count(imgs[i]->get_image_type()) >= 3 ? d.z : 1u };
+				CHECK(imgs[i]->write(*queue, wants[i].data(), l0_size, { 0, 0, 0 }, extent, { 0, 0 }, { 0, 0 }));
+			}
+			for (auto& img : imgs) CHECK(img->generate_mip_map_chain_async(*queue));
+			for (auto& img : imgs) CHECK(img->generate_mip_map_chain_async(*queue)); // and again: the same images are still in the open run
+			queue->fence();
+			for (size_t i = 0; i < imgs.size(); ++i) {
+				std::vector<uint8_t> got(wants[i].size());
+				CHECK(imgs[i]->read_levels(*queue, got.data(), got.size(), 0, imgs[i]->get_mip_level_count() - 1));
+				CHECK(got == wants[i]);
+			}
+		}
+		queue->set_mip_chain_overlap(false);
 	}
 	// provide_minify_program (device_image.cpp:155-194): a context-registered program receives the chains of that context's images
 	{
