@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -259,38 +260,45 @@ bool pdl_enabled() {
 // Opt-in per stream, because work the caller enqueues on the stream behind the library's back cannot be seen here (the caller
 // announces it with flmip_stream_fence).
 struct stream_run {
+	// held from the decision about a chain's first kernel until the chain is noted (flmip_mip_chain_generate_from), and by whatever closes
+	// the run: the bookkeeping must see chains and closers of one stream in ONE order even when several host threads enqueue on it.  A
+	// closer takes it BEFORE it enqueues its own work, so its work lands behind every chain noted so far; chains decided after the
+	// close find an empty run and wait at their start, wherever they land relative to the closer's work.
+	std::mutex mtx;
 	bool enabled = false;
 	std::vector<const void*> images; // compared by address only
 };
-std::mutex runs_mtx;
-std::unordered_map<CUstream, stream_run> runs;
+std::mutex runs_mtx; // guards the map only
+std::unordered_map<CUstream, std::shared_ptr<stream_run>> runs;
 std::atomic<uint32_t> overlap_streams { 0 }; // streams that have opted in (0: every hook below returns at once)
 constexpr size_t MAX_RUN_IMAGES = 64;
 
-void run_close(CUstream stream) {
-	if (overlap_streams.load(std::memory_order_relaxed) == 0) return;
+std::shared_ptr<stream_run> run_of(CUstream stream, bool create = false) {
+	if (!create && overlap_streams.load(std::memory_order_relaxed) == 0) return nullptr;
 	std::lock_guard<std::mutex> lock(runs_mtx);
 	auto it = runs.find(stream);
-	if (it != runs.end()) it->second.images.clear();
+	if (it != runs.end()) return it->second;
+	if (!create) return nullptr;
+	return runs.emplace(stream, std::make_shared<stream_run>()).first->second;
 }
-// may the first kernel of a chain on `img` start without waiting for the kernel in front of it?
-bool run_allows_late_head(CUstream stream, const void* img) {
-	if (overlap_streams.load(std::memory_order_relaxed) == 0) return false;
-	std::lock_guard<std::mutex> lock(runs_mtx);
-	auto it = runs.find(stream);
-	if (it == runs.end() || !it->second.enabled) return false;
-	const std::vector<const void*>& v = it->second.images;
+void run_close(CUstream stream) {
+	if (auto r = run_of(stream)) {
+		std::lock_guard<std::mutex> lock(r->mtx);
+		r->images.clear();
+	}
+}
+// may the first kernel of a chain on `img` start without waiting for the kernel in front of it?  (r->mtx held)
+bool run_allows_late_head(const stream_run& r, const void* img) {
+	if (!r.enabled) return false;
+	const std::vector<const void*>& v = r.images;
 	if (v.empty() || v.size() >= MAX_RUN_IMAGES) return false; // nothing of ours in front / bound the bookkeeping
 	return std::find(v.begin(), v.end(), img) == v.end();
 }
-// after a chain of `kernels` launches on `img`, the first of which started late (or not)
-void run_note_chain(CUstream stream, const void* img, uint32_t kernels, bool late_head) {
-	if (overlap_streams.load(std::memory_order_relaxed) == 0 || kernels == 0) return;
-	std::lock_guard<std::mutex> lock(runs_mtx);
-	auto it = runs.find(stream);
-	if (it == runs.end() || !it->second.enabled) return;
-	if (!(late_head && kernels == 1)) it->second.images.clear(); // an early-waiting kernel opened a new run
-	it->second.images.push_back(img);
+// after a chain of `kernels` launches on `img`, the first of which started late (or not)  (r->mtx held)
+void run_note_chain(stream_run& r, const void* img, uint32_t kernels, bool late_head) {
+	if (!r.enabled || kernels == 0) return;
+	if (!(late_head && kernels == 1)) r.images.clear(); // an early-waiting kernel opened a new run
+	r.images.push_back(img);
 }
 // The chain head's late-wait flag travels to whichever launcher enqueues the chain's first kernel.
 thread_local bool tl_late_head = false;
@@ -1013,20 +1021,23 @@ int flmip_overlap_bookkeeping(uint64_t stream, uint64_t image, uint32_t op, uint
 	const void* img = reinterpret_cast<const void*>(image);
 	switch (op) {
 		case 0: {
-			std::lock_guard<std::mutex> lock(runs_mtx);
-			stream_run& r = runs[s];
-			if ((arg != 0) != r.enabled) {
-				r.enabled = arg != 0;
-				if (r.enabled) overlap_streams.fetch_add(1, std::memory_order_relaxed);
+			const std::shared_ptr<stream_run> r = run_of(s, true);
+			std::lock_guard<std::mutex> lock(r->mtx);
+			if ((arg != 0) != r->enabled) {
+				r->enabled = arg != 0;
+				if (r->enabled) overlap_streams.fetch_add(1, std::memory_order_relaxed);
 				else overlap_streams.fetch_sub(1, std::memory_order_relaxed);
 			}
-			r.images.clear();
+			r->images.clear();
 			return 0;
 		}
 		case 1:
 		case 2: {
-			const bool late = op == 1 && run_allows_late_head(s, img);
-			run_note_chain(s, img, arg, late);
+			const std::shared_ptr<stream_run> r = run_of(s);
+			if (!r) return 0;
+			std::lock_guard<std::mutex> lock(r->mtx);
+			const bool late = op == 1 && run_allows_late_head(*r, img);
+			run_note_chain(*r, img, arg, late);
 			return late ? 1 : 0;
 		}
 		case 3: run_close(s); return 0;
@@ -1034,7 +1045,10 @@ int flmip_overlap_bookkeeping(uint64_t stream, uint64_t image, uint32_t op, uint
 			std::lock_guard<std::mutex> lock(runs_mtx);
 			auto it = runs.find(s);
 			if (it != runs.end()) {
-				if (it->second.enabled) overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+				std::lock_guard<std::mutex> rl(it->second->mtx);
+				if (it->second->enabled) overlap_streams.fetch_sub(1, std::memory_order_relaxed);
+				it->second->enabled = false;
+				it->second->images.clear();
 				runs.erase(it);
 			}
 			return 0;
@@ -1648,16 +1662,19 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 	// chain overlap (opt-in per stream): the first kernel of this chain may start without waiting for the kernel in front of it when
 	// that one belongs to a chain on another image; only the PDL kernels know how (not the literal kernel, not a recorded graph)
 	const bool head_is_pdl_kernel = (img->fast && first_level == 0) || img->tiled;
-	const bool late_head = head_is_pdl_kernel && !tl_recorder && pdl_enabled() && run_allows_late_head((CUstream)stream, img);
+	const std::shared_ptr<stream_run> run = tl_recorder ? nullptr : run_of((CUstream)stream);
+	std::unique_lock<std::mutex> run_lock;
+	if (run) run_lock = std::unique_lock<std::mutex>(run->mtx);
+	const bool late_head = run && head_is_pdl_kernel && pdl_enabled() && run_allows_late_head(*run, img);
 	tl_late_head = late_head;
 	tl_chain_launches = 0;
-	struct chain_note {
-		flmip_image img; CUstream stream; bool late;
+	struct chain_note { // runs before run_lock is released (declared after it)
+		flmip_image img; stream_run* run; bool late;
 		~chain_note() {
 			tl_late_head = false;
-			if (!tl_recorder) run_note_chain(stream, img, tl_chain_launches, late);
+			if (run) run_note_chain(*run, img, tl_chain_launches, late);
 		}
-	} note { img, (CUstream)stream, late_head };
+	} note { img, run.get(), late_head };
 	uint32_t next = first_level + 1; // first level still to be produced
 	if (img->fast && first_level == 0) {
 		CUfunction fn = nullptr;

@@ -162,3 +162,43 @@ def test_overlap_across_queues_and_batches(gpu_ctx, overlap_queue, oracle_mod):
     batch.destroy()
     for im in imgs:
         im.destroy()
+
+
+def test_overlap_with_several_host_threads_on_one_queue(gpu_ctx, overlap_queue, oracle_mod):
+    """four host threads enqueue chains on their own images, fences and events on ONE overlapping queue at the same time: the bookkeeping
+    sees chains and closers in one order per stream (stream_run::mtx), every image ends bit-exact"""
+    import threading
+    ctx, dev, _ = gpu_ctx
+    q = overlap_queue
+    t = T.IMAGE_2D | T.RGBA8 | M
+    dims = [(1024, 1024), (512, 1024), (1000, 600), (2048, 512), (256, 256), (1024, 512), (640, 480), (512, 512)]
+    imgs, wants = [], []
+    for i, dim in enumerate(dims):
+        im = ctx.create_image(q, dim, t)
+        l0 = oracle_mod.fill_synthetic(dim, t, 80 + i)
+        im.upload_levels(q, l0, 0, 0)
+        imgs.append(im); wants.append(oracle_mod.generate_mip_map_chain(l0, dim, t, threads=8))
+    errors = []
+
+    def worker(k):
+        try:
+            rng = np.random.default_rng(k)
+            mine = imgs[2 * k: 2 * k + 2]
+            for step in range(400):
+                r = rng.random()
+                if r < 0.05:
+                    q.fence()
+                elif r < 0.08:
+                    floor_b200.lib().flmip_event_destroy(dev.index, q.record_event())
+                mine[int(rng.integers(0, 2))].enqueue_mip_map_chain(q)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [th.start() for th in threads]
+    [th.join() for th in threads]
+    assert not errors, errors
+    for im, want, dim in zip(imgs, wants, dims):
+        assert np.array_equal(im.download_levels(q), want), dim
+    for im in imgs:
+        im.destroy()
