@@ -123,7 +123,13 @@ def shard_layers(total: int, world: int, rank: int, multiple: int = 1):
     return lo * multiple, (hi - lo) * multiple
 
 
+def shard_round_robin(total: int, world: int, rank: int):
+    """batches of independent textures: texture i goes to rank i % world"""
+    return list(range(rank, total, world))
+
+
 L2_BYTES = 126 << 20
+BATCH_TEXTURES = 512  # the batch leg: independent 1024^2 RGBA8 textures (C1's shape), round-robin over the ranks
 
 
 def workload_geometry(workload: str, world: int = 1, rank: int = 0, layers_override: int = 0):
@@ -337,6 +343,76 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
             "kernel": ("flmip_fast%dd_k*" if plan["single_pass"] else "flmip_tile%dd_k*") % (3 if (t >> 16) & 3 == 3 else 2)}
 
 
+def time_batch(ctx, dev, q, ranks, rank, world, steps, warmup, peak):
+    """The third way the path shards (north star: "array layers, cube faces and batches of independent textures"): BATCH_TEXTURES
+    independent 1024^2 RGBA8 textures, texture i on rank i % world, no collective.  A step = the chains of all of this rank's textures,
+    timed three ways on the device: stream-ordered chains on a plain queue, the same calls on a queue with chain overlap, and one CUDA
+    graph per step (flmip_batch_*).  16 sampled textures per rank are compared with the oracle on every level."""
+    import oracle
+    desc, dim, t, _, cid = WORKLOADS["c1"]
+    mine = shard_round_robin(BATCH_TEXTURES, world, rank)
+    imgs = []
+    for g in mine:
+        im = ctx.create_image(q, dim, t)
+        im.fill_synthetic(q, cid, g)
+        imgs.append(im)
+    q.finish()
+    alg = imgs[0].image_data_size_mip_maps * len(imgs)
+    blocker = ctx.create_image(q, (8192, 8192), T.IMAGE_2D | T.RGBA16F | M)
+    blocker.fill_synthetic(q, 2, 0)
+    qo = ctx.create_queue(dev)
+    qo.set_mip_chain_overlap(True)
+    batch = ctx.create_mip_chain_batch(imgs)
+
+    def timed(Q, step_fn, behind_blocker):
+        for _ in range(max(1, warmup)):
+            step_fn(Q)
+        ranks.barrier(Q)
+        if behind_blocker:
+            # a host thread needs longer to enqueue a chain than the GPU to run it: queue the steps behind ~3 ms of untimed work so that
+            # the events time the device and not the enqueue loop (one graph launch per step needs no such help)
+            for _ in range(28):
+                blocker.enqueue_mip_map_chain(Q)
+        e0 = Q.record_event()
+        for _ in range(steps):
+            step_fn(Q)
+        e1 = Q.record_event()
+        ms = Q.elapsed_ms(e0, e1) / steps
+        ranks.barrier(Q)
+        ms_all, = ranks.reduce([ms], "max")
+        return ms_all
+
+    def chains(Q):
+        for im in imgs:
+            im.enqueue_mip_map_chain(Q)
+
+    ms_queued = timed(q, chains, True)
+    ms_overlapped = timed(qo, chains, True)
+    ms_graph = timed(q, lambda Q: batch.enqueue(Q), False)
+    total, = ranks.reduce([alg], "sum")
+    # what did the timed launches write?
+    picks = sampled_layers(len(imgs))
+    mism = 0
+    for k in picks:
+        got = imgs[k].download_levels(q)
+        l0 = oracle.fill_synthetic(dim, t, cid, layer_id0=mine[k])
+        if not (np.array_equal(got[: l0.size], l0) and np.array_equal(got, oracle.generate_mip_map_chain(l0, dim, t, threads=min(os.cpu_count() or 8, 32)))):
+            mism += 1
+    mism_all, checked = ranks.reduce([mism, len(picks)], "sum")
+    batch.destroy()
+    for im in imgs + [blocker]:
+        im.destroy()
+    qo.destroy()
+    leg = lambda ms: {"value": round(total / (ms * 1e-3) / 1e9, 2), "ms_per_step": round(ms, 5), "us_per_texture": round(ms * 1e3 / len(imgs), 3),
+                      "frac": round(total / world / (ms * 1e-3) / 1e9 / peak, 4)}
+    return {"workload": "B1: batch of %d independent 1024x1024 RGBA8 textures, texture i on rank i %% N" % BATCH_TEXTURES, "unit": "GB/s", "scaling": "strong",
+            "textures_per_gpu": len(imgs), "algorithmic_bytes_per_gpu_step": alg, "steps": steps,
+            "queued": leg(ms_queued), "overlapped": leg(ms_overlapped), "graph": leg(ms_graph),
+            "parity_check": {"layers_checked": int(checked), "mismatches": int(mism_all), "scope": "16 sampled textures per rank (first, last, seeded), every level, bit-exact vs oracle"},
+            "note": "queued = one chain per texture on a plain queue (stream-ordered); overlapped = the same calls on a queue with flmip_stream_set_chain_overlap; "
+                    "graph = one CUDA graph launch per step (flmip_batch_*); queued / overlapped steps are enqueued behind ~3 ms of untimed work so that the events time the device, not the host's enqueue loop"}
+
+
 def pcie_probe(q, img, pin_in, pin_out, h2d, d2h, last, ranks, reps=6):
     """the ceiling of the end-to-end leg: the same copies through the same C-ABI calls with no kernel between them -- upload alone,
     read-back alone, and both directions at once (two queues), every rank at the same time (max over ranks)"""
@@ -444,6 +520,11 @@ def run_ours(args, rank, world, local_rank):
                            "algorithmic_bytes_per_gpu_step": L["alg_bytes"], "per_gpu_achieved": round(L["achieved"], 2), "frac": round(L["achieved"] / peak, 4),
                            "launches_per_step": L["plan"]["launches"], "kernel": L["kernel"], "parity_check": L["parity_check"],
                            "limiter": "fixed per-launch cost (launch + ring ramp-up + last-CTA tail of the group / layer stages), paid once per step whatever the shard size"}
+
+        try:
+            layered["b1"] = time_batch(ctx, dev, q, ranks, rank, world, max(3, min(args.steps, 10)), 2, peak)
+        except floor_b200.FlmipError as e:
+            layered["b1"] = {"unavailable": str(e)[:200]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

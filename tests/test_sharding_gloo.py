@@ -23,6 +23,16 @@ def test_shard_layers_partitions_exactly():
                 assert lo + n == lo2 and lo % mult == 0 and n % mult == 0
 
 
+def test_shard_round_robin_partitions_exactly():
+    """batches of independent textures: texture i on rank i % N -- every texture exactly once, shares differ by at most one"""
+    for total in (512, 7, 1, 64):
+        for world in (1, 2, 3, 4, 8):
+            shares = [bench.shard_round_robin(total, world, r) for r in range(world)]
+            assert sorted(i for sh in shares for i in sh) == list(range(total))
+            assert max(len(sh) for sh in shares) - min(len(sh) for sh in shares) <= 1
+            assert all(i % world == r for r, sh in enumerate(shares) for i in sh)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
