@@ -339,7 +339,8 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
     ms_per_step = ms_all / steps
     return {"images": rot[:keep], "fill_ids": fill_ids[:keep], "rdim": rdim, "alg_bytes": alg_bytes, "levels": levels, "plan": plan, "ms_rank": ms, "ms_per_step": ms_per_step,
             "value": total_bytes / (ms_per_step * 1e-3) / 1e9, "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "total_bytes": total_bytes,
-            "mtexels_in_per_s": total_texels / (ms_per_step * 1e-3) / 1e6, "launches": int(launches), "clocks": clocks, "parity_check": pc, "n_rot": n_rot, "pipelined": pipelined,
+            "mtexels_in_per_s": total_texels / (ms_per_step * 1e-3) / 1e6,
+            "mtexels_out_per_s": (total_bytes / img.get_bytes_per_pixel() - total_texels) / (ms_per_step * 1e-3) / 1e6, "launches": int(launches), "clocks": clocks, "parity_check": pc, "n_rot": n_rot, "pipelined": pipelined,
             "kernel": ("flmip_fast%dd_k*" if plan["single_pass"] else "flmip_tile%dd_k*") % (3 if (t >> 16) & 3 == 3 else 2)}
 
 
@@ -563,7 +564,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": round(R["ms_per_step"], 6), "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
             "config": config_for(args.workload, world, args.layers),
-            "detail": {"mtexels_in_per_s": round(R["mtexels_in_per_s"], 1), "single_pass": plan["single_pass"], "launches_per_step": plan["launches"],
+            "detail": {"mtexels_in_per_s": round(R["mtexels_in_per_s"], 1), "mtexels_out_per_s": round(R["mtexels_out_per_s"], 1), "single_pass": plan["single_pass"], "launches_per_step": plan["launches"],
                        "images_in_rotation": R["n_rot"]},
             "roofline": {"bound": "hbm", "achieved": round(R["achieved"], 2), "peak": peak, "unit": "GB/s", "frac": round(R["achieved"] / peak, 4),
                          "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src, "kernel": R["kernel"], "algorithmic_bytes_per_launch": alg_bytes},
