@@ -45,3 +45,6 @@ def test_cpp_bench_program_runs(built_lib):
     assert res.returncode == 0, res.stdout + res.stderr
     gbs = float(res.stdout.split("enqueued")[1].split("=")[1].split("GB/s")[0])
     assert gbs > 1000.0, res.stdout
+    # the overlapped leg (device_queue::set_mip_chain_overlap) must not be slower than stream-ordered chains
+    over = float(res.stdout.split("overlapped")[1].split("=")[1].split("GB/s")[0])
+    assert over > 0.98 * gbs, res.stdout
