@@ -1,5 +1,6 @@
 #!/bin/bash
-# late-wait experiment: chains on different images start without waiting for the chain before them (FLMIP_LATE_WAIT_EXPERIMENT=1)
+# (round 2, historical) first late-wait experiment: FLMIP_LATE_WAIT_EXPERIMENT only exists with profiles/r2/08_tail_split_experiment.patch applied;
+# the adopted form is flmip_stream_set_chain_overlap (scripts/r2_overlap.sh, bench.py key "pipelined")
 mkdir -p gpurun_out/r2lw
 export FLMIP_LIB=$PWD/build/variants/lib_lw.so
 run() { # name, workload, env...

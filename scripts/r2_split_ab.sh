@@ -1,5 +1,6 @@
 #!/bin/bash
-# tail split of the single-pass kernel: parity first, then FLMIP_TAIL_SPLIT (split units per 100 resident CTAs) over the workloads
+# (round 2, historical) tail split of the single-pass kernel: FLMIP_TAIL_SPLIT only exists with profiles/r2/08_tail_split_experiment.patch applied
+# (measured and not adopted: profiles/r2/08_tail_split_ab.txt); parity first, then FLMIP_TAIL_SPLIT (split units per 100 resident CTAs) over the workloads
 mkdir -p gpurun_out/r2split
 timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -x -q -m gpu -k "tail_split or single_pass or slot_hand_off or baseline_configs or c3_full" 2>&1 | tail -5
 run() { # name, workload, env...
