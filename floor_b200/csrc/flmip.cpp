@@ -1799,9 +1799,9 @@ extern "C" int flmip_debug_timeline(flmip_image img, uint64_t* out, uint32_t cta
 	WITH_DEVICE(img->device)
 	const uint64_t sched = img->fast ? img->fast_params.sched : img->pcounters + (uint64_t)img->layers * sizeof(uint32_t);
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((sched + 15ull) & ~7ull), (size_t)ctas * 8u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
+	CU_TRY(cu.p_cuMemcpyDtoHAsync(out, ((sched + 15ull) & ~7ull), (size_t)ctas * 16u * sizeof(uint64_t), nullptr), "cuMemcpyDtoH(timeline)");
 	CU_TRY(cu.p_cuStreamSynchronize(nullptr), "cuStreamSynchronize");
-	CU_TRY(cu.p_cuMemsetD8Async(((sched + 15ull) & ~7ull), 0, (size_t)ctas * 8u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
+	CU_TRY(cu.p_cuMemsetD8Async(((sched + 15ull) & ~7ull), 0, (size_t)ctas * 16u * sizeof(uint64_t), nullptr), "cuMemsetD8(timeline)");
 	return FLMIP_OK;
 }
 #endif

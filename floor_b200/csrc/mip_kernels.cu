@@ -602,8 +602,8 @@ __device__ __forceinline__ uint64_t gtime() {
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
-#define FLMIP_STAMP(P, slot) (reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 8u + (slot)] = gtime())
-#define FLMIP_STAMP_MAX(P, slot) atomicMax(&reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 8u + (slot)], (unsigned long long)gtime())
+#define FLMIP_STAMP(P, slot) (reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 16u + (slot)] = gtime())
+#define FLMIP_STAMP_MAX(P, slot) atomicMax(&reinterpret_cast<unsigned long long*>(((P).sched + 15ull) & ~7ull)[blockIdx.x * 16u + (slot)], (unsigned long long)gtime())
 #else
 #define FLMIP_STAMP(P, slot) ((void)0)
 #define FLMIP_STAMP_MAX(P, slot) ((void)0)
@@ -640,7 +640,7 @@ template <int DIMS> __device__ __forceinline__ bool next_level_has_texels(const 
 // All region sizes are powers of two, so texel indices decompose with shifts.
 template <uint32_t EK, int CH, int DIMS>
 __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Region& R, const flmip_fast_params& P, uint32_t layer,
-											 uint32_t lane) {
+											 uint32_t lane, uint32_t stamp_slot = 0u) {
 	constexpr int BPP = Codec<EK>::BYTES * CH;
 	using IO = TexelIO<BPP>;
 	while (R.lvl + 1 < P.level_count && R.w >= 2 && R.h >= 2 && (DIMS < 3 || R.d >= 2)) {
@@ -662,6 +662,9 @@ __device__ __forceinline__ void cascade_warp(uint8_t*& src, uint8_t*& dst, Regio
 		__syncwarp();
 		uint8_t* t = src; src = dst; dst = t;
 		R.w = dw; R.h = dh; R.d = dd; R.ox = ox; R.oy = oy; R.oz = oz; R.lvl = L;
+#ifdef FLMIP_TIMELINE
+		if (stamp_slot && stamp_slot < 16u && lane == 0) FLMIP_STAMP_MAX(P, stamp_slot++); // tuning builds: one stamp per level
+#endif
 	}
 }
 
@@ -833,7 +836,7 @@ __device__ __forceinline__ void finish_group(uint8_t* patch_a, uint8_t* patch_b,
 	uint8_t *src = patch_a, *dst = patch_b;
 	gather_region<BPP, DIMS>(src, R, P, layer, lane);
 	if (lane == 0) FLMIP_STAMP_MAX(P, 5); // group patch gathered
-	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane);
+	cascade_warp<EK, CH, DIMS>(src, dst, R, P, layer, lane, 8u);
 	if (lane == 0) FLMIP_STAMP_MAX(P, 6); // group patch reduced
 
 	// ---- layer stage: the last group of a layer finishes the chain -----------------------------------------

@@ -18,7 +18,7 @@ for name, dim, t in [("c2", (8192, 8192), T.IMAGE_2D | T.RGBA16F | M), ("c5", (5
         imgs[k & 1].enqueue_mip_map_chain(q)
     q.finish()
     n = 296
-    buf = np.zeros((n, 8), np.uint64)
+    buf = np.zeros((n, 16), np.uint64)
     L.flmip_debug_timeline(imgs[0]._handle, buf.ctypes.data, n)   # clears the stamps
     e0 = q.record_event()
     imgs[0].enqueue_mip_map_chain(q)
@@ -42,6 +42,7 @@ for name, dim, t in [("c2", (8192, 8192), T.IMAGE_2D | T.RGBA16F | M), ("c5", (5
         order = np.argsort(rel[ran][:, 6])[-4:]
         for row in rel[ran][order]:
             print(f"   group stage of a CTA: consumers done {row[2]:7.1f} | publish returned {row[4]:7.1f} gathered {row[5]:7.1f} reduced {row[6]:7.1f}"
-                  + (f" | layer stage done {row[7]:7.1f}" if row[7] > 0 else ""))
+                  + (f" | layer stage done {row[7]:7.1f}" if row[7] > 0 else "")
+                  + " | levels of the group patch at " + " ".join(f"{v:.2f}" for v in row[8:16] if v > 0))
     for im in imgs:
         im.destroy()

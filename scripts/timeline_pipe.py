@@ -22,7 +22,7 @@ for name, dim, t in [("c2", (8192, 8192), T.IMAGE_2D | T.RGBA16F | M), ("c5", (5
         imgs[k % nimg].enqueue_mip_map_chain(q)
     q.finish()
     n = 296
-    buf = np.zeros((n, 8), np.uint64)
+    buf = np.zeros((n, 16), np.uint64)
     for im in imgs:
         L.flmip_debug_timeline(im._handle, buf.ctypes.data, n)   # clears the stamps
     e0 = q.record_event()

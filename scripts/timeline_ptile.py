@@ -24,7 +24,7 @@ for name, dim, t, limit in [("n1 2 levels only", (3840, 2160), T.IMAGE_2D | T.RG
     e1 = q.record_event()
     rate = q.elapsed_ms(e0, e1) / 24
     n = 296
-    buf = np.zeros((n, 8), np.uint64)
+    buf = np.zeros((n, 16), np.uint64)
     L.flmip_debug_timeline(imgs[0]._handle, buf.ctypes.data, n)   # clears the stamps
     e0 = q.record_event()
     imgs[0].enqueue_mip_map_chain(q)
