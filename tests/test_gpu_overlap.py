@@ -31,6 +31,8 @@ FAMILY = [
     (T.IMAGE_2D | T.RGBA8, (1000, 600)), (T.IMAGE_2D | T.RGBA8, (3840, 2160)), (T.IMAGE_2D_ARRAY | T.RGBA16F, (1920, 1080, 24)),
     (T.IMAGE_3D | T.RGBA8, (100, 60, 40)), (T.IMAGE_1D | T.R32F, (4097,)), (T.IMAGE_2D | T.RGB8, (640, 480)),
 ]
+# per-image creation arguments: the two forms of the persistent TMA tile kernel (two levels per launch / the whole chain in one launch)
+FAMILY_KW = {6: {"tma_tiles": "always"}, 8: {"tma_tiles": "always+nosplit"}}
 
 
 def test_overlapped_chains_are_bit_exact_in_any_order(gpu_ctx, overlap_queue, oracle_mod):
@@ -41,7 +43,9 @@ def test_overlapped_chains_are_bit_exact_in_any_order(gpu_ctx, overlap_queue, or
     imgs, l0s = [], []
     for i, (bt, dim) in enumerate(FAMILY):
         t = bt | M
-        im = ctx.create_image(q, dim, t)
+        im = ctx.create_image(q, dim, t, **FAMILY_KW.get(i, {}))
+        if i in FAMILY_KW:
+            assert im.plan()["tma_tile_launches"] >= 1, (dim, im.plan())
         l0 = oracle_mod.fill_synthetic(dim, t, 700 + i)
         im.upload_levels(q, l0, 0, 0, sync=False)
         imgs.append(im); l0s.append(l0)
@@ -98,7 +102,7 @@ def test_completion_follows_stream_order(gpu_ctx, overlap_queue, oracle_mod, big
 def test_overlap_is_real_and_off_by_default(gpu_ctx, oracle_mod):
     """16 independent 1024^2 RGBA8 textures, 8 rounds of chains back to back: microseconds per chain on a default queue and on a queue with
     overlap (measured on a B200: 9.5 vs 3.9 us); a fence before every chain brings the default behaviour back.  The host needs about as
-    long to enqueue a chain as the GPU to run it, so the chains are enqueued behind 3 ms of other work (chains on a large image) and the
+    long to enqueue a chain as the GPU to run it, so the chains are enqueued behind 6 ms of other work (chains on a large image) and the
     events bracket what the GPU then finds queued up: device time, not enqueue time."""
     ctx, dev, _ = gpu_ctx
     t = T.IMAGE_2D | T.RGBA8 | M
@@ -116,8 +120,8 @@ def test_overlap_is_real_and_off_by_default(gpu_ctx, oracle_mod):
         best = 1e9
         for rep in range(4):
             q.finish()
-            for _ in range(28):
-                blocker.enqueue_mip_map_chain(q)   # ~3 ms of GPU work: the 128 small chains below are enqueued long before it ends
+            for _ in range(56):
+                blocker.enqueue_mip_map_chain(q)   # ~6 ms of GPU work: the 128 small chains below are enqueued long before it ends
             e0 = q.record_event()
             for k in range(8 * len(imgs)):
                 if mode == "overlap+fence":
