@@ -297,19 +297,24 @@ bool run_allows_late_head(const stream_run& r, const void* img) {
 	if (v.empty() || v.size() >= MAX_RUN_IMAGES) return false; // nothing of ours in front / bound the bookkeeping
 	return std::find(v.begin(), v.end(), img) == v.end();
 }
-// after a chain of `kernels` launches on `img`, the first of which started late (or not)  (r->mtx held)
+// after a chain of `kernels` launches on `img`, the first of which started late (or not)  (r->mtx held).  Only a first kernel that
+// waited at its start opens a new run: the later kernels of a chain on an overlapping queue release their dependents BEFORE they wait
+// (mode 2 of pdl_start), so they say nothing about what has completed by the time the next kernel starts.
 void run_note_chain(stream_run& r, const void* img, uint32_t kernels, bool late_head) {
 	if (!r.enabled || kernels == 0) return;
-	if (!(late_head && kernels == 1)) r.images.clear(); // an early-waiting kernel opened a new run
+	if (!late_head) r.images.clear();
 	r.images.push_back(img);
 }
-// The chain head's late-wait flag travels to whichever launcher enqueues the chain's first kernel.
-thread_local bool tl_late_head = false;
+// The chain's launch modes travel to the launchers through the calling thread: the first kernel of a chain takes the head's mode (0 or 1),
+// every later one mode 2 on an overlapping queue and 0 otherwise (see pdl_start in mip_kernels.cu).
+thread_local bool tl_late_head = false, tl_overlap_chain = false, tl_head_taken = false;
 thread_local uint32_t tl_chain_launches = 0; // kernels the calling thread has enqueued since flmip_mip_chain_generate_from reset it
-uint32_t take_late_head() {
-	const bool v = tl_late_head;
-	tl_late_head = false;
-	return v ? 1u : 0u;
+uint32_t take_launch_mode() {
+	if (!tl_head_taken) {
+		tl_head_taken = true;
+		return tl_late_head ? 1u : 0u;
+	}
+	return tl_overlap_chain ? 2u : 0u;
 }
 
 // While a batch is being built (flmip_batch_create) the launches of the calling thread are recorded as kernel nodes of a CUDA
@@ -754,7 +759,7 @@ int launch_tile_levels(flmip_image_s& im, device_state* ds, uint32_t src_level, 
 		T.tiles[2] = im.dc == 3 ? (T.dim[0][2] + FLMIP_TILE3D_Z - 1u) / FLMIP_TILE3D_Z : 1u;
 		T.layers = im.layers;
 		T.no_double = im.no_double;
-		T.late_wait = take_late_head();
+		T.late_wait = take_launch_mode();
 		for (uint32_t k = 2; k <= T.nlev; ++k)
 			for (uint32_t d = 0; d < im.dc; ++d)
 				if (axis_reads_texel_2(im.levels[s + k - 1u].dim[d])) T.block_sync = 1u;
@@ -911,7 +916,7 @@ int launch_ptile(flmip_image_s& im, device_state* ds, uint32_t src, const ptile_
 	P.total_tiles = P.tiles[0] * P.tiles[1] * im.layers;
 	P.stages = 2;
 	P.no_double = im.no_double;
-	P.late_wait = take_late_head();
+	P.late_wait = take_launch_mode();
 	// units of 4 tiles (one publish per unit) once every resident CTA has many tiles to work through; below that the pool keeps up
 	// with one publish per tile, and units would only coarsen what the scheduler can balance
 	const uint64_t resident_ctas = 2ull * ds->info.units;
@@ -1670,11 +1675,14 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 	if (run) run_lock = std::unique_lock<std::mutex>(run->mtx);
 	const bool late_head = run && head_is_pdl_kernel && pdl_enabled() && run_allows_late_head(*run, img);
 	tl_late_head = late_head;
+	tl_overlap_chain = run && run->enabled && pdl_enabled();
+	tl_head_taken = false;
 	tl_chain_launches = 0;
 	struct chain_note { // runs before run_lock is released (declared after it)
 		flmip_image img; stream_run* run; bool late;
 		~chain_note() {
-			tl_late_head = false;
+			tl_late_head = tl_overlap_chain = false;
+			tl_head_taken = true; // launches outside a chain (fills, ...) never take a chain's mode
 			if (run) run_note_chain(*run, img, tl_chain_launches, late);
 		}
 	} note { img, run.get(), late_head };
@@ -1684,7 +1692,7 @@ int flmip_mip_chain_generate_from(flmip_image img, uint32_t first_level, flmip_s
 		int rc = get_function(ds, img->fast_name, img->fast_smem, &fn);
 		if (rc != FLMIP_OK) return rc;
 		flmip_fast_params P = img->fast_params;
-		P.late_wait = take_late_head();
+		P.late_wait = take_launch_mode();
 		void* args[] = { &img->tmap, &P };
 		rc = launch(fn, img->fast_grid, FLMIP_BLOCK_THREADS, img->fast_smem, (CUstream)stream, args, true);
 		if (rc != FLMIP_OK) return rc;

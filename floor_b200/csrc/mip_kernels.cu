@@ -583,15 +583,22 @@ __device__ __forceinline__ void pdl_wait_then_release() {
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-// Chains of independent images (`late_wait`, set by the host when the kernel before this one in the stream is a chain on ANOTHER image and
-// the queue has opted in: flmip_stream_set_chain_overlap): nothing this kernel reads or writes is touched by its predecessor, so it starts
-// streaming while that kernel's tail (last units, group / layer stages: 7 - 10 us without memory traffic) is still running, and its own
-// dependents may follow as soon as its CTAs are resident.  Stream order for whatever comes after is kept by waiting for the predecessor
-// at the END instead (pdl_late_wait, one thread of one CTA: a grid is complete when its last CTA is), so a grid never completes before
-// the grid in front of it has completed and flushed.
+// Chains of independent images (`late_wait`, set per launch by the host on queues that have opted in: flmip_stream_set_chain_overlap).
+//   0: wait for the kernel in front, then release the dependents (above).
+//   1: the kernel in front is a chain on ANOTHER image (none of the kernels that can still be running touches this image): nothing this
+//      kernel reads or writes depends on it, so it starts streaming while that kernel's tail (last units, group / layer stages: 7 - 10 us
+//      without memory traffic) is still running, and its own dependents may follow as soon as its CTAs are resident.  Stream order for
+//      whatever comes after is kept by waiting for the predecessor at the END instead (pdl_late_wait, one thread of one CTA: a grid is
+//      complete when its last CTA is), so a grid never completes before the grid in front of it has completed and flushed.
+//   2: a later kernel of a multi-kernel chain on such a queue: it needs its predecessor's output, so it waits at its start -- but it
+//      releases its dependents first, so that the first kernel of the NEXT image's chain need not wait for this (small) kernel either.
 __device__ __forceinline__ void pdl_start(uint32_t late_wait) {
-	if (late_wait) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-	else pdl_wait_then_release();
+	if (late_wait == 0u) {
+		pdl_wait_then_release();
+	} else {
+		asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+		if (late_wait == 2u) asm volatile("griddepcontrol.wait;" ::: "memory");
+	}
 }
 __device__ __forceinline__ void pdl_late_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -2353,7 +2360,7 @@ extern "C" __global__ void __launch_bounds__(256) flmip_fill(const __grid_consta
 	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_fast##D##d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,    \
 																					   const __grid_constant__ flmip_fast_params P) { \
 		fast_body<K, CHN, D>(tmap, P);                                                                                          \
-		if (P.late_wait && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                                \
+		if (P.late_wait == 1u && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                             \
 	}
 #define FLMIP_FAST_KERNELS_FOR_KIND(K) \
 	FLMIP_FAST_KERNEL(2, K, 1) FLMIP_FAST_KERNEL(2, K, 2) FLMIP_FAST_KERNEL(2, K, 4) FLMIP_FAST_KERNEL(3, K, 1) FLMIP_FAST_KERNEL(3, K, 2) FLMIP_FAST_KERNEL(3, K, 4)
@@ -2380,7 +2387,7 @@ FLMIP_FAST_KERNELS_FOR_KIND(11)
 	extern "C" __global__ void __launch_bounds__(FLMIP_BLOCK_THREADS, 2) flmip_ptile2d_k##K##_c##CHN(const __grid_constant__ CUtensorMap tmap,     \
 																							   const __grid_constant__ flmip_ptile_params P) { \
 		ptile_body<K, CHN>(tmap, P);                                                                                                \
-		if (P.late_wait && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                                    \
+		if (P.late_wait == 1u && blockIdx.x == 0 && threadIdx.x == 0) pdl_late_wait();                                                 \
 	}
 #define FLMIP_PTILE_KERNELS_FOR_KIND(K) FLMIP_PTILE_KERNEL(K, 1) FLMIP_PTILE_KERNEL(K, 2) FLMIP_PTILE_KERNEL(K, 4)
 #ifdef FLMIP_DEV_ONLY
@@ -2418,7 +2425,7 @@ FLMIP_PTILE_KERNELS_FOR_KIND(11)
 #define FLMIP_TILE_KERNEL(D, K, CHN)                                                                                              \
 	extern "C" __global__ void __launch_bounds__(256, FLMIP_TILE_MIN_BLOCKS(D, K, CHN)) flmip_tile##D##d_k##K##_c##CHN(const __grid_constant__ flmip_tile_params P) { \
 		tile_body<K, CHN, D>(P);                                                                                                 \
-		if (P.late_wait && blockIdx.x == gridDim.x - 1u && threadIdx.x == 0) pdl_late_wait();                                    \
+		if (P.late_wait == 1u && blockIdx.x == gridDim.x - 1u && threadIdx.x == 0) pdl_late_wait();                                 \
 	}
 #define FLMIP_TILE_KERNELS_FOR_KIND(K) \
 	FLMIP_TILE_KERNEL(2, K, 1) FLMIP_TILE_KERNEL(2, K, 2) FLMIP_TILE_KERNEL(2, K, 4) FLMIP_TILE_KERNEL(3, K, 1) FLMIP_TILE_KERNEL(3, K, 2) FLMIP_TILE_KERNEL(3, K, 4) \

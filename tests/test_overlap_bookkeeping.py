@@ -15,8 +15,8 @@ class Model:
     def chain(self, img, kernels, pdl_head=True):
         late = self.enabled and pdl_head and bool(self.run) and len(self.run) < 64 and img not in self.run
         if self.enabled and kernels:
-            if not (late and kernels == 1):
-                self.run = []
+            if not late:
+                self.run = []      # only a first kernel that waited at its start opens a new run (later kernels release their dependents first)
             self.run.append(img)
         return late
 
@@ -38,7 +38,8 @@ def test_overlap_is_off_by_default_and_per_stream(built_lib):
     L.flmip_overlap_bookkeeping(s1, 0, OTHER, 0)               # a copy / fill / event / fence
     assert L.flmip_overlap_bookkeeping(s1, 5, CHAIN, 1) == 0   # ... closes the run
     assert L.flmip_overlap_bookkeeping(s1, 6, CHAIN, 3) == 1   # a three-kernel chain may start late ...
-    assert L.flmip_overlap_bookkeeping(s1, 5, CHAIN, 1) == 1   # ... but its later kernels waited: the run is {6}, image 5 is out of it
+    assert L.flmip_overlap_bookkeeping(s1, 5, CHAIN, 1) == 0   # ... and its later kernels release their dependents before they wait: image 5 is still in the run
+    assert L.flmip_overlap_bookkeeping(s1, 6, CHAIN, 1) == 1   # that chain waited at its start and opened a new run {5}
     assert L.flmip_overlap_bookkeeping(s1, 6, CHAIN, 1) == 0
     assert L.flmip_overlap_bookkeeping(s1, 7, LITERAL_CHAIN, 2) == 0   # a chain the literal kernel starts never skips the wait
     assert L.flmip_overlap_bookkeeping(s1, 8, CHAIN, 1) == 1
@@ -89,7 +90,7 @@ def test_a_late_head_never_shares_an_image_with_the_open_run(built_lib):
         late = L.flmip_overlap_bookkeeping(s, img, CHAIN, kernels)
         if late:
             assert img not in maybe_running, step
-        if not late or kernels > 1:
-            maybe_running = set()      # a kernel of this chain waited for everything in front of it
+        if not late:
+            maybe_running = set()      # the first kernel of this chain waited for everything in front of it before anything behind it could start
         maybe_running.add(img)
     L.flmip_overlap_bookkeeping(s, 0, FORGET, 0)
