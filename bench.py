@@ -282,6 +282,20 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
         clocks["window"] = ("the timed region (%.1f ms) followed by %.0f ms of the same steps, untimed, so that the 100 ms sampler sees this load"
                             % (ms, (time.perf_counter() - t_s) * 1e3))
     ranks.barrier(q)
+    # per-step spread ("report median and min"): the same steps once more with an event behind every step.  Not the headline:
+    # an event between two chains keeps the second from being launched as a programmatic dependent of the first, so each of these
+    # steps pays its launch in full (this rank's numbers).
+    evs = [q.record_event()]
+    for i in range(steps):
+        rot[(i + 1) % n_rot].enqueue_mip_map_chain(q)
+        evs.append(q.record_event())
+    q.finish()
+    per = sorted(q.elapsed_ms(a, b, destroy=False) for a, b in zip(evs, evs[1:]))
+    for e in evs:
+        lib.flmip_event_destroy(dev.index, e)
+    per_step = {"median_ms": round(per[len(per) // 2], 6), "min_ms": round(per[0], 6), "max_ms": round(per[-1], 6),
+                "note": "one event behind every step: no programmatic dependent launch between consecutive chains"}
+    ranks.barrier(q)
     # the same steps on a queue that lets chains on independent images overlap (flmip_stream_set_chain_overlap): the first kernel of a
     # chain starts while the chain in front of it is still finishing, and waits for it before it ends.  Reported beside `value`, which
     # stays the strictly stream-ordered number.  Rotates over 8 images: a chain waits as before when its image still has a kernel in
@@ -340,7 +354,7 @@ def time_resident(ctx, dev, q, ranks, rank, world, workload, steps, warmup, laye
     return {"images": rot[:keep], "fill_ids": fill_ids[:keep], "rdim": rdim, "alg_bytes": alg_bytes, "levels": levels, "plan": plan, "ms_rank": ms, "ms_per_step": ms_per_step,
             "value": total_bytes / (ms_per_step * 1e-3) / 1e9, "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9, "total_bytes": total_bytes,
             "mtexels_in_per_s": total_texels / (ms_per_step * 1e-3) / 1e6,
-            "mtexels_out_per_s": (total_bytes / img.get_bytes_per_pixel() - total_texels) / (ms_per_step * 1e-3) / 1e6, "launches": int(launches), "clocks": clocks, "parity_check": pc, "n_rot": n_rot, "pipelined": pipelined,
+            "mtexels_out_per_s": (total_bytes / img.get_bytes_per_pixel() - total_texels) / (ms_per_step * 1e-3) / 1e6, "launches": int(launches), "clocks": clocks, "parity_check": pc, "n_rot": n_rot, "pipelined": pipelined, "per_step": per_step,
             "kernel": ("flmip_fast%dd_k*" if plan["single_pass"] else "flmip_tile%dd_k*") % (3 if (t >> 16) & 3 == 3 else 2)}
 
 
@@ -565,7 +579,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": DTYPE[args.workload], "data": "synthetic (counter-based splitmix64, SURVEY 8d)",
             "config": config_for(args.workload, world, args.layers),
             "detail": {"mtexels_in_per_s": round(R["mtexels_in_per_s"], 1), "mtexels_out_per_s": round(R["mtexels_out_per_s"], 1), "single_pass": plan["single_pass"], "launches_per_step": plan["launches"],
-                       "images_in_rotation": R["n_rot"]},
+                       "images_in_rotation": R["n_rot"], "per_step": R["per_step"]},
             "roofline": {"bound": "hbm", "achieved": round(R["achieved"], 2), "peak": peak, "unit": "GB/s", "frac": round(R["achieved"] / peak, 4),
                          "traffic": dram_traffic_per_launch(args.workload), "peak_source": peak_src, "kernel": R["kernel"], "algorithmic_bytes_per_launch": alg_bytes},
             "parity_check": R["parity_check"],
